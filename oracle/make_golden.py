@@ -1,0 +1,241 @@
+"""
+ORACLE — TEST INFRASTRUCTURE ONLY (build-container only).
+
+Generates `tests/golden/*.npz` by running the UNMODIFIED reference (`/root/reference`) through
+`oracle/ref_shim.py`.  Run from the repo root:   python oracle/make_golden.py
+
+Weights come from `musediff_oracle.make_random_params(seed, ...)` (numpy PCG64, so the tests can
+re-create them without torch RNG), loaded into the reference module with `load_state_dict`.
+Noise: `torch.randn_like` is monkey-patched for the duration of a reference call so that it draws
+from `musediff_oracle.NoiseStream(seed)`; the oracle mirrors the reference's call order, so both
+consume identical noise and whole loops become comparable.
+"""
+import os
+import sys
+import types
+from functools import partial
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+import musediff_oracle as O  # noqa: E402
+from ref_shim import install_reference_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def to_torch_state(p):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in p.items()}
+
+
+def build_reference(p, seq_len, diffusion_steps=2000, noise_schedule="sqrt", timestep_respacing="",
+                    rescale_timesteps=True, predict_xstart=True):
+    import torch
+    from MuseDiffusion.utils.initialization import create_model_and_diffusion
+    args = types.SimpleNamespace(hidden_dim=128, hidden_t_dim=128, vocab_size=729, seq_len=seq_len, dropout=0.1,
+                                 noise_schedule=noise_schedule, diffusion_steps=diffusion_steps,
+                                 timestep_respacing=timestep_respacing, rescale_timesteps=rescale_timesteps,
+                                 predict_xstart=predict_xstart)
+    model, diffusion = create_model_and_diffusion(args)
+    missing = model.load_state_dict(to_torch_state(p), strict=True)
+    model.eval().requires_grad_(False)
+    model_emb = torch.nn.Embedding(num_embeddings=729, embedding_dim=128, padding_idx=0,
+                                   _weight=model.word_embedding.weight.clone().cpu())
+    model_emb.eval().requires_grad_(False)
+    return model, diffusion, model_emb
+
+
+class patched_randn_like:
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        import torch
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **kw: torch.from_numpy(self.stream.randn(tuple(x.shape)))
+        return self
+
+    def __exit__(self, *a):
+        import torch
+        torch.randn_like = self.orig
+
+
+def golden_schedules():
+    from MuseDiffusion.models import diffusion as D
+    out = {}
+    names = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+             "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+             "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+    for sched, T, resp in [("sqrt", 2000, ""), ("linear", 1000, ""), ("cosine", 500, ""), ("trunc_cos", 400, ""),
+                           ("trunc_lin", 300, ""), ("pw_lin", 200, ""), ("sqrt", 2000, "ddim50"),
+                           ("sqrt", 300, "10,15,20")]:
+        betas = D.get_named_beta_schedule(sched, T)
+        use = D.space_timesteps(T, resp if resp else [T])
+        d = D.SpacedDiffusion(use_timesteps=use, betas=betas, rescale_timesteps=True, predict_xstart=True)
+        key = "%s_%d_%s" % (sched, T, resp.replace(",", "-") or "full")
+        out[key + "/raw_betas"] = betas
+        out[key + "/timestep_map"] = np.asarray(d.timestep_map, dtype=np.int64)
+        for n in names:
+            out[key + "/" + n] = np.asarray(getattr(d, n), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **out)
+    print("schedules.npz", len(out), "arrays")
+
+
+def golden_rounding():
+    import torch
+    from MuseDiffusion.models.rounding import get_efficient_knn, denoised_fn_round
+    rng = np.random.default_rng(7)
+    E = rng.standard_normal((729, 128)).astype(np.float32)
+    E[700] = E[5]                                           # duplicate rows -> tie -> lowest index
+    E[300] = E[12]
+    x = rng.standard_normal((6, 37, 128)).astype(np.float32) * 0.7
+    x[0, 0] = E[700]                                        # exact hits (distance ~0 before clamp)
+    x[0, 1] = E[300] + 1e-4
+    x[1, 2] = 0.0
+    x[2, :5] = E[[0, 728, 1, 5, 12]]
+    val, idx = get_efficient_knn(torch.from_numpy(E), torch.from_numpy(x.reshape(-1, 128)))
+    emb = torch.nn.Embedding(729, 128, _weight=torch.from_numpy(E.copy()))
+    new = denoised_fn_round(emb, torch.from_numpy(x), None)
+    np.savez_compressed(os.path.join(OUT, "rounding.npz"), E=E, x=x, idx=idx[0].numpy(), val=val[0].numpy(),
+                        rounded=new.detach().numpy())
+    print("rounding.npz")
+
+
+def golden_forward(seq_len, B, seed, fname, tvals):
+    import torch
+    p = O.make_random_params(seed=seed, seq_len=seq_len)
+    model, diffusion, _ = build_reference(p, seq_len)
+    rng = np.random.default_rng(seed + 100)
+    x = rng.standard_normal((B, seq_len, 128)).astype(np.float32)
+    t = np.asarray(tvals, dtype=np.float32)
+    with torch.no_grad():
+        out = model(torch.from_numpy(x), torch.from_numpy(t)).numpy()
+        emb_t = model.time_embed(model.timestep_embedding(torch.from_numpy(t), 128)).numpy()
+        logits = model.get_logits(torch.from_numpy(x)).numpy()
+    np.savez_compressed(os.path.join(OUT, fname), seed=seed, seq_len=seq_len, x=x, t=t, model_output=out,
+                        emb_t=emb_t, tokens=logits.argmax(-1))
+    print(fname, out.shape, float(np.abs(out).mean()))
+
+
+def golden_steps(seq_len=64, B=3, seed=3):
+    """single p_sample / ddim_sample / q_sample calls on the reference with injected noise."""
+    import torch
+    p = O.make_random_params(seed=seed, seq_len=seq_len)
+    model, diffusion, model_emb = build_reference(p, seq_len)
+    rng = np.random.default_rng(seed + 200)
+    cond = O.make_synthetic_batch("modification", B, seq_len, seed=seed)
+    ids = torch.from_numpy(cond["input_ids"])
+    x_start = model.get_embeds(ids)
+    mask = torch.broadcast_to(torch.from_numpy(cond["input_mask"]).unsqueeze(-1), x_start.shape)
+    out = {"seed": seed, "seq_len": seq_len, "input_ids": cond["input_ids"], "input_mask": cond["input_mask"]}
+    for tag, tval in [("t1999", 1999), ("t1000", 1000), ("t1", 1), ("t0", 0)]:
+        x = torch.from_numpy(rng.standard_normal((B, seq_len, 128)).astype(np.float32))
+        x = torch.where(mask == 0, x_start, x)
+        t = torch.tensor([tval] * B)
+        stream = O.NoiseStream(seed * 1000 + tval)
+        with patched_randn_like(stream), torch.no_grad():
+            r = diffusion.p_sample(model, x, t, clip_denoised=True,
+                                   denoised_fn=partial(__import__("MuseDiffusion.models.rounding", fromlist=["x"]).denoised_fn_round, model_emb, dist=None),
+                                   model_kwargs={}, top_p=1, mask=mask, x_start=x_start)
+        out[tag + "/x"] = x.numpy()
+        out[tag + "/p_sample"] = r["sample"].numpy()
+        out[tag + "/pred_xstart"] = r["pred_xstart"].numpy()
+        out[tag + "/model_output"] = diffusion._wrap_model(model)(x, t).numpy()
+        stream = O.NoiseStream(seed * 1000 + tval + 1)
+        with patched_randn_like(stream), torch.no_grad():
+            r2 = diffusion.ddim_sample(model, x, t, clip_denoised=True,
+                                       denoised_fn=partial(__import__("MuseDiffusion.models.rounding", fromlist=["x"]).denoised_fn_round, model_emb, dist=None),
+                                       model_kwargs={}, mask=mask, x_start=x_start, eta=0.0)
+        out[tag + "/ddim_sample"] = r2["sample"].numpy()
+        # unclamped / unrounded variants (denoised_fn=None, clip_denoised False) with top_p=0
+        stream = O.NoiseStream(seed * 1000 + tval + 2)
+        with patched_randn_like(stream), torch.no_grad():
+            r3 = diffusion.p_sample(model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs={},
+                                    top_p=0, mask=None, x_start=None)
+        out[tag + "/p_sample_raw"] = r3["sample"].numpy()
+    # q_sample as run/sample.py:195-197 calls it
+    stream = O.NoiseStream(seed * 1000 + 77)
+    with patched_randn_like(stream):
+        tq = torch.full((B, 1), 74)
+        xq = diffusion.q_sample(x_start.unsqueeze(-1), tq, mask=mask).squeeze(-1)
+    out["q_sample_t74"] = xq.numpy()
+    np.savez_compressed(os.path.join(OUT, "steps_tiny.npz"), **out)
+    print("steps_tiny.npz")
+
+
+def golden_loop(fname, mode, seq_len, B, seed, diffusion_steps, step, strength=0.75, top_p=1):
+    """run/sample.py:177-220 replayed with reference objects (the data loader / MIDI tail are out of scope)."""
+    import torch
+    from MuseDiffusion.models.rounding import denoised_fn_round
+    p = O.make_random_params(seed=seed, seq_len=seq_len)
+    model, diffusion, model_emb = build_reference(p, seq_len, diffusion_steps=diffusion_steps)
+    cond = O.make_synthetic_batch(mode, B, seq_len, seed=seed + 5)
+    ids = torch.from_numpy(cond["input_ids"])
+    mask_ori = torch.from_numpy(cond["input_mask"])
+    stream = O.NoiseStream(seed + 999)
+    if step == diffusion_steps:
+        gap, sample_fn = 1, diffusion.p_sample_loop
+    else:
+        gap, sample_fn = diffusion_steps // step, diffusion.ddim_sample_loop
+    with patched_randn_like(stream), torch.no_grad():
+        x_start = model.get_embeds(ids)
+        input_ids_mask = torch.broadcast_to(mask_ori.unsqueeze(dim=-1), x_start.shape)
+        if mode == "generation":
+            noising_t = None
+            noise = torch.randn_like(x_start)
+            x_noised = torch.where(torch.eq(input_ids_mask, 0), x_start, noise)
+        else:
+            noising_t = int(step * strength)
+            timestep = torch.full((B, 1), noising_t - 1)
+            x_noised = diffusion.q_sample(x_start.unsqueeze(-1), timestep, mask=input_ids_mask).squeeze(-1)
+        samples = sample_fn(model=model, shape=(B, seq_len, 128), noise=x_noised, clip_denoised=True,
+                            denoised_fn=partial(denoised_fn_round, model_emb, dist=None), model_kwargs=cond,
+                            top_p=top_p, clamp_step=0, clamp_first=True, mask=input_ids_mask, x_start=x_start,
+                            gap=gap, t_enc=noising_t, only_last=True)
+        sample = samples[-1]
+        tokens = torch.argmax(model.get_logits(sample), dim=-1)
+    np.savez_compressed(os.path.join(OUT, fname), seed=seed, seq_len=seq_len, mode=mode,
+                        diffusion_steps=diffusion_steps, step=step, strength=strength, top_p=top_p,
+                        input_ids=cond["input_ids"], input_mask=cond["input_mask"], x_noised=x_noised.numpy(),
+                        final_sample=sample.numpy(), tokens=tokens.numpy())
+    print(fname, tokens.shape, tokens[0, :20].tolist())
+
+
+def golden_meta_prefix():
+    """README example meta -> 27-token prefix through the real MetaToSequence."""
+    from MuseDiffusion.utils.decode_util import meta_to_batch
+    meta = {"bpm": 70, "audio_key": "aminor", "time_signature": "4/4", "pitch_range": "mid_high",
+            "num_measures": 8, "inst": "acoustic_piano", "genre": "newage", "min_velocity": 60,
+            "max_velocity": 80, "track_role": "main_melody", "rhythm": "standard",
+            "chord_progression": "-".join(["Am"] * 8 + ["G"] * 8 + ["F"] * 8 + ["E"] * 8) + "-" +
+                                 "-".join(["Am"] * 8 + ["G"] * 8 + ["F"] * 8 + ["E"] * 8)}
+    b = meta_to_batch(meta, batch_size=2, seq_len=64)
+    np.savez_compressed(os.path.join(OUT, "meta_batch.npz"), input_ids=b["input_ids"].numpy(),
+                        input_mask=b["input_mask"].numpy())
+    print("meta_batch.npz", b["input_ids"][0, :30].tolist())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    install_reference_shim()
+    import torch
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    golden_schedules()
+    golden_rounding()
+    golden_meta_prefix()
+    golden_forward(64, 2, 1, "forward_tiny.npz", [999.5, 3.0])
+    golden_forward(200, 1, 2, "forward_ragged.npz", [500.0])          # L not a multiple of 64/128
+    golden_forward(2096, 1, 4, "forward_base.npz", [250.0])           # the base-config shape
+    golden_steps()
+    golden_loop("loop_gen_ddpm.npz", "generation", 64, 2, 11, 40, 40)
+    golden_loop("loop_mod_ddpm.npz", "modification", 64, 3, 12, 40, 40, strength=0.75)
+    golden_loop("loop_mod_ddim.npz", "modification", 64, 2, 13, 2000, 20, strength=1.0)
+    golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
+
+
+if __name__ == "__main__":
+    main()
