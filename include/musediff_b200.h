@@ -1,0 +1,122 @@
+/*
+ * musediff_b200 — C-ABI of the B200-native MuseDiffusion reverse-diffusion sampling path.
+ *
+ * The reference (YAIxPOZAlabs/MuseDiffusion) has no FFI of its own: its boundary is the Python call surface
+ * exercised by MuseDiffusion/run/sample.py.  These entry points are what a ctypes binding
+ * placed behind that surface calls; each cites the reference code it replaces (paths relative to the reference
+ * root).  Conventions: plain device pointers + sizes, no torch types, no allocation, no internal threads, work is
+ * enqueued on the caller's `stream`; return 0 (MD_OK) or a negative code, text via md_last_error().
+ * All tensors are contiguous row-major; "M" is the token count B*L.
+ */
+#ifndef MUSEDIFF_B200_H
+#define MUSEDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define MD_OK 0
+#define MD_ERR_ARG (-1)
+#define MD_ERR_CUDA (-2)
+
+/* epilogues of md_linear_bf16 */
+#define MD_EPI_BIAS 0          /* y = xW^T + b                                                           */
+#define MD_EPI_BIAS_GELU 1     /* erf-GELU(y)            HF BertIntermediate (called from network.py:151) */
+#define MD_EPI_BIAS_TANH 2     /* tanh(y)                input_up_proj / output_down_proj, network.py:69-70,83-84 */
+#define MD_EPI_BIAS_RESID 3    /* y + residual           HF BertSelfOutput / BertOutput pre-LayerNorm sum */
+#define MD_EPI_BIAS_POS_TIME 4 /* y + pos[l] + temb[b]   network.py:146-148 pre-LayerNorm sum            */
+
+/* modes of md_posterior_step */
+#define MD_STEP_DDPM 0 /* GaussianDiffusion.p_sample,    models/diffusion.py:349-404 */
+#define MD_STEP_DDIM 1 /* GaussianDiffusion.ddim_sample, models/diffusion.py:701-757 */
+
+#define MD_MAX_CONST_T 2048 /* schedules up to this length live in __constant__ memory */
+
+const char* md_last_error(void);
+int md_abi_version(void);
+
+/* ---- schedule tables: GaussianDiffusion.__init__ (models/diffusion.py:136-185) + _extract_into_tensor (:904-917).
+ * `tables` = 9 host arrays of T floats each (float64 tables already cast to fp32 exactly as diffusion.py:914 does):
+ *   0 posterior_mean_coef1   1 posterior_mean_coef2   2 model_log_variance (fixed-large, :313-317)
+ *   3 sqrt_recip_alphas_cumprod   4 sqrt_recipm1_alphas_cumprod   5 alphas_cumprod   6 alphas_cumprod_prev
+ *   7 sqrt_alphas_cumprod    8 sqrt_one_minus_alphas_cumprod
+ * Uploads them to device memory (and rows 0..6 to __constant__ memory when T <= MD_MAX_CONST_T). */
+int md_set_schedule(const float* tables, int T, cudaStream_t stream);
+
+/* ---- elementwise / small kernels ---- */
+/* fp32 -> bf16 cast of the state x_t (A operand of the first Linear).  n elements. */
+int md_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);
+/* TransformerNetModel.get_embeds (models/network.py:88-89): out[m, :] = E[ids[m], :].  ids int32 or int64. */
+int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out, int64_t M, int V, int D,
+                    cudaStream_t stream);
+/* timestep_embedding + time_embed MLP (models/network.py:108-129, 60-65, 139):
+ * out[b, :] = W2 silu(W0 [cos(t f), sin(t f)] + b0) + b2, fp32 throughout.  t is the float fed to the model. */
+int md_timestep_mlp(const float* t, const float* W0, const float* b0, const float* W2, const float* b2, float* out,
+                    int B, int t_dim, int mid_dim, int out_dim, cudaStream_t stream);
+/* LayerNorm over the last dim of a bf16 [M, H] tensor, fp32 statistics (network.py:149 and the HF Bert
+ * LayerNorms, eps = 1e-12).  H must be a multiple of 256 and <= 2048. */
+int md_layernorm_bf16(const void* in_bf16, const float* gamma, const float* beta, float eps, void* out_bf16,
+                      int64_t M, int H, cudaStream_t stream);
+
+/* ---- dense contractions (tcgen05 / TMEM / TMA) ---- */
+/* nn.Linear with fused epilogue: out[M,N] = epi(A[M,K] W[N,K]^T + bias).  A, W bf16; bias/pos/temb fp32;
+ * out bf16 (out_is_f32 = 0) or fp32.  resid: bf16 [M,N] (MD_EPI_BIAS_RESID).  pos: [L,N], temb: [M/L or 1, N] with
+ * row stride temb_stride (0 = one shared row) (MD_EPI_BIAS_POS_TIME).  K, N multiples of 8. */
+int md_linear_bf16(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epilogue,
+                   int out_is_f32, const void* resid, const float* pos, const float* temb, int temb_stride, int L,
+                   cudaStream_t stream);
+/* HF BertSelfAttention without mask (called from network.py:151): qkv bf16 [B*L, 3*NH*DH] laid out
+ * [q heads | k heads | v heads] per token, q already scaled by 1/sqrt(DH); out bf16 [B*L, NH*DH] = softmax(qk^T) v.
+ * DH must be 64. */
+int md_attention_bf16(const void* qkv, void* out, int B, int L, int NH, int DH, cudaStream_t stream);
+
+/* ---- rounding / decode ---- */
+/* get_efficient_knn (models/rounding.py:21-28): idx[m] = argmin_v clamp(|E_v|^2 + |x_m|^2 - 2 E_v.x_m, 0),
+ * lowest v on ties.  x fp32 [M,D], E fp32 [V,D], idx int32 [M]; margin (optional, fp32 [M]) = second-best minus
+ * best distance.  D must be 128. */
+int md_round_argmin(const float* x, const float* E, int32_t* idx, float* margin, int64_t M, int V, int D,
+                    cudaStream_t stream);
+/* get_logits + argmax (models/network.py:91-93, run/sample.py:219-220): tok[m] = argmax_v (x_m.E_v + bias_v). */
+int md_logits_argmax(const float* x, const float* E, const float* bias, int32_t* tok, float* margin, int64_t M, int V,
+                     int D, cudaStream_t stream);
+
+/* ---- the fused per-step posterior update ----
+ * x_{t-1} from x_t for mode DDPM (p_sample :349-404 with p_mean_variance :311-347, q_posterior_mean :257-278) or
+ * DDIM (ddim_sample :701-757, _predict_eps_from_xstart :201-205):
+ *   pred  = idx ? E[idx] : pred_in                      (denoised_fn_round, rounding.py:31-47)
+ *   pred  = clip ? clamp(pred, -1, 1) : pred            (diffusion.py:323-324, AFTER rounding)
+ *   DDPM: x' = c1[t] pred + c2[t] x_t + [t != 0] exp(0.5 logvar[t]) n
+ *   DDIM: eps = (sr[t] x_t - pred)/srm1[t]; sigma = eta sqrt((1-abp)/(1-ab)) sqrt(1-ab/abp);
+ *         x' = pred sqrt(abp) + sqrt(1-abp-sigma^2) eps + [t != 0] sigma n
+ *   x'   = mask == 0 ? x_start : x'                     (diffusion.py:394-397, 752-755)
+ * n = noise[m, d] if noise != NULL, else a counter-based Philox4x32-10 normal keyed by (seed, step_counter, global
+ * element index (seq_offset*L + m)*D + d), truncated to |n| <= top_p by inverse-CDF when top_p > 0 (the law the
+ * reference's rejection loop :378-385 samples).  t: int32 [B] schedule index per sequence.  mask: int32, indexed
+ * m*mask_tok_stride + d*mask_d_stride (NULL = no mask).  out_bf16 (optional) receives a bf16 copy of x'. */
+int md_posterior_step(const float* x_t, const int32_t* idx, const float* pred_in, const float* E, const float* noise,
+                      uint64_t seed, uint64_t step_counter, int64_t seq_offset, const int32_t* t, const int32_t* mask,
+                      int64_t mask_tok_stride, int64_t mask_d_stride, const float* x_start, float* x_out, void* out_bf16,
+                      int B, int L, int D, int mode, float eta, int clip, float top_p, cudaStream_t stream);
+/* x0 = sqrt_recip[t] x_t - sqrt_recipm1[t] eps  (_predict_xstart_from_eps, diffusion.py:194-199), for
+ * predict_xstart = False models. */
+int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D,
+                       cudaStream_t stream);
+/* q_sample (diffusion.py:229-255): out = mask==0 ? x0 : sqrt_ab[t] x0 + sqrt_1m_ab[t] n.  t < 0 means "pure
+ * noise": out = mask==0 ? x0 : n (the generation-mode initialisation, run/sample.py:190-193).  Noise as above. */
+int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
+                const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride, float* out,
+                void* out_bf16, int B, int L, int D, cudaStream_t stream);
+/* standard-normal / truncated-normal fill with the same Philox stream (testing + generation init). */
+int md_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t step_counter, int64_t elem_offset, float top_p,
+                   cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSEDIFF_B200_H */

@@ -1,0 +1,339 @@
+// Fused non-causal, unmasked multi-head attention for the BERT-style encoder of the denoiser (sm_100a).
+//
+//   ctx[b, l, h, :] = softmax_j( q[b, l, h, :] . k[b, j, h, :] ) v[b, j, h, :]        (q pre-scaled by 1/sqrt(64))
+//
+// Replaces HF BertSelfAttention's eager softmax(QK^T/sqrt(d))V (transformers modeling_bert.py, called from the
+// reference at MuseDiffusion/models/network.py:151 with hidden states only: no attention mask, no head mask), which
+// materialises [B, 12, L, L] fp32 scores in HBM.  Here the scores never leave the SM:
+//   * S = Q K^T by tcgen05.mma (SS) into TMEM, one 128x128 fp32 tile per Q tile,
+//   * each softmax thread owns one row of S (tcgen05.ld 32x32b), keeps the running max / sum in registers, writes
+//     P = exp2(..) as packed bf16 back over S in TMEM,
+//   * O += P V by tcgen05.mma with A = P from TMEM (TS form), B = V tile (MN-major, 128B swizzle) from shared memory,
+//   * O is rescaled lazily in TMEM only when the row max grew by more than 2^8 (exact after final normalisation).
+// One persistent CTA per SM works on TWO 128-row Q tiles of the same (b, h) so the tensor pipe computes S for one
+// tile while the other tile's softmax runs, and both tiles share every K/V stage brought in by TMA.
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = softmax/correction/epilogue for Q tile 0, warps 6..9 = same for Q tile 1.
+#include "common.cuh"
+#include "musediff_b200.h"
+
+namespace md {
+int num_sms();
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                      uint64_t stride2_elems, uint32_t box0, uint32_t box1);
+
+constexpr int ATT_BQ = 128;        // rows per Q tile
+constexpr int ATT_BKV = 128;       // keys per K/V stage
+constexpr int ATT_DH = 64;
+constexpr int ATT_STAGES = 3;
+constexpr int kAttThreads = 320;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
+constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;   // TMEM columns
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;   // log2 units
+
+struct AttArgs {
+    int B, L, NH;
+    int n_pairs;        // ceil(ceil(L/128) / 2)
+    int n_qtiles;       // ceil(L/128)
+    int n_kv;           // ceil(L/128)
+    int total_work;     // B * NH * n_pairs
+    __nv_bfloat16* out; // [B*L, NH*64]
+};
+
+struct Work { int b, h, pair; };
+MD_DEVINL Work decode_work(int w, const AttArgs& a) {
+    Work r;
+    r.pair = w % a.n_pairs;
+    const int bh = w / a.n_pairs;
+    r.h = bh % a.NH;
+    r.b = bh / a.NH;
+    return r;
+}
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                     // 2 tiles
+    uint8_t* sK = smem + 2 * ATT_TILE_BYTES;                // ATT_STAGES tiles
+    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // ATT_STAGES tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;                // [1]
+    uint64_t* q_empty = bars + 1;           // [1]
+    uint64_t* k_full = bars + 2;            // [STAGES]
+    uint64_t* k_empty = k_full + ATT_STAGES;
+    uint64_t* v_full = k_empty + ATT_STAGES;
+    uint64_t* v_empty = v_full + ATT_STAGES;
+    uint64_t* s_full = v_empty + ATT_STAGES;   // [2]
+    uint64_t* p_full = s_full + 2;             // [2]
+    uint64_t* o_full = p_full + 2;             // [2]
+    uint64_t* o_empty = o_full + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int H = a.NH * ATT_DH;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(&s_full[x], 1);
+            mbar_init(&p_full[x], 128);
+            mbar_init(&o_full[x], 1);
+            mbar_init(&o_empty[x], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            uint32_t wcnt = 0, kcnt = 0;
+            for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
+                const Work wk = decode_work(w, a);
+                const int qt0 = wk.pair * 2;
+                const int n_active = (qt0 + 1 < a.n_qtiles) ? 2 : 1;
+                mbar_wait(q_empty, (wcnt & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full, n_active * ATT_TILE_BYTES);
+                for (int x = 0; x < n_active; ++x)
+                    tma_load_3d(sQ + x * ATT_TILE_BYTES, &tmQKV, q_full, wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
+                for (int j = 0; j < a.n_kv; ++j, ++kcnt) {
+                    const int st = kcnt % ATT_STAGES;
+                    const uint32_t ph = (kcnt / ATT_STAGES) & 1;
+                    mbar_wait(&k_empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+                    tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &k_full[st], H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
+                    mbar_wait(&v_empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+                    tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &v_full[st], 2 * H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, ATT_DH, 1);   // B (= V) is MN-major
+            const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
+            const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
+            uint32_t wcnt = 0, kcnt = 0;
+            uint32_t pcnt[2] = {0, 0};   // completed P tiles per Q tile (phase of p_full)
+            uint32_t ocnt[2] = {0, 0};   // work items per Q tile (phase of o_empty)
+            auto issue_qk = [&](int x, int st) {
+                const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
+                const uint64_t kd = make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(tS[x], qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+                tc_commit(&s_full[x]);
+            };
+            auto issue_pv = [&](int x, int st, bool accumulate) {
+                const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < ATT_BKV / 16; ++k)   // 16 keys = 8 packed TMEM columns of P, 2048 B of V rows
+                    umma_ts(tO[x], tS[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+            };
+            for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
+                const Work wk = decode_work(w, a);
+                const int n_active = (wk.pair * 2 + 1 < a.n_qtiles) ? 2 : 1;
+                mbar_wait(q_full, wcnt & 1);
+                {   // S(0) for both tiles
+                    const int st = kcnt % ATT_STAGES;
+                    mbar_wait(&k_full[st], (kcnt / ATT_STAGES) & 1);
+                    tc_fence_after();
+                    for (int x = 0; x < n_active; ++x) issue_qk(x, st);
+                    tc_commit(&k_empty[st]);
+                }
+                for (int j = 0; j < a.n_kv; ++j) {
+                    const int st = (kcnt + j) % ATT_STAGES;
+                    const uint32_t ph = ((kcnt + j) / ATT_STAGES) & 1;
+                    const int st_n = (kcnt + j + 1) % ATT_STAGES;
+                    const uint32_t ph_n = ((kcnt + j + 1) / ATT_STAGES) & 1;
+                    const bool has_next = (j + 1 < a.n_kv);
+                    mbar_wait(&v_full[st], ph);
+                    if (has_next) mbar_wait(&k_full[st_n], ph_n);
+                    for (int x = 0; x < n_active; ++x) {
+                        if (j == 0) mbar_wait(&o_empty[x], (ocnt[x] & 1) ^ 1);   // previous item's O drained
+                        mbar_wait(&p_full[x], pcnt[x] & 1);
+                        ++pcnt[x];
+                        tc_fence_after();
+                        issue_pv(x, st, j > 0);
+                        if (!has_next) { tc_commit(&o_full[x]); ++ocnt[x]; }
+                        if (has_next) issue_qk(x, st_n);     // S(j+1) of this tile while the other tile's softmax runs
+                    }
+                    tc_commit(&v_empty[st]);
+                    if (has_next) tc_commit(&k_empty[st_n]);
+                }
+                tc_commit(q_empty);
+                kcnt += a.n_kv;
+            }
+        }
+    } else {
+        // =========================================================== softmax / correction / epilogue
+        const int x = (warp - 2) >> 2;          // which Q tile this warpgroup owns
+        const int quad = warp & 3;              // TMEM lane quadrant
+        const int r = quad * 32 + lane;         // row inside the Q tile
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0) + lane_addr;
+        const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0) + lane_addr;
+        uint32_t scnt = 0, ocnt = 0;
+        for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+            const Work wk = decode_work(w, a);
+            const int qt = wk.pair * 2 + x;
+            if (qt >= a.n_qtiles) continue;
+            float m_used = 0.f, l_sum = 0.f;
+            for (int j = 0; j < a.n_kv; ++j, ++scnt) {
+                mbar_wait(&s_full[x], scnt & 1);
+                tc_fence_after();
+                uint32_t s[128];
+                {
+                    uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                    uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                    uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+                    uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+                    tmem_ld32(tS + 0, s0);
+                    tmem_ld32(tS + 32, s1);
+                    tmem_ld32(tS + 64, s2);
+                    tmem_ld32(tS + 96, s3);
+                }
+                tc_wait_ld();
+                const int valid = a.L - j * ATT_BKV;   // keys in this block that exist
+                if (valid < ATT_BKV) {
+#pragma unroll
+                    for (int c = 0; c < 128; ++c)
+                        if (c >= valid) s[c] = 0xff800000u;   // -inf
+                }
+                float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+                      mx3 = __uint_as_float(s[3]);
+#pragma unroll
+                for (int c = 4; c < 128; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                }
+                const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;
+                if (j == 0) {
+                    m_used = mb;
+                } else {
+                    const bool need = mb > m_used + kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // lazy rescale of the running output (and sum) held in TMEM
+                        const float f = need ? fast_exp2(m_used - mb) : 1.0f;
+                        if (need) m_used = mb;
+                        l_sum *= f;
+                        uint32_t o0[32], o1[32];
+                        tmem_ld32(tO, o0);
+                        tmem_ld32(tO + 32, o1);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            o0[c] = __float_as_uint(__uint_as_float(o0[c]) * f);
+                            o1[c] = __float_as_uint(__uint_as_float(o1[c]) * f);
+                        }
+                        tmem_st32(tO, o0);
+                        tmem_st32(tO + 32, o1);
+                    }
+                }
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(s[g * 32 + 2 * c]), kLog2e, -m_used));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(s[g * 32 + 2 * c + 1]), kLog2e, -m_used));
+                        if (c & 1) { acc2 += p0; acc3 += p1; } else { acc0 += p0; acc1 += p1; }
+                        pk[c] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st16(tS + g * 16, pk);    // P overwrites the first 64 columns of S (row already in registers)
+                }
+                l_sum += (acc0 + acc1) + (acc2 + acc3);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[x]);
+            }
+            // ---- epilogue: O / l -> bf16 -> global
+            mbar_wait(&o_full[x], ocnt & 1);
+            ++ocnt;
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tO, o0);
+            tmem_ld32(tO + 32, o1);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&o_empty[x]);
+            const int row = qt * ATT_BQ + r;
+            if (row < a.L) {
+                const float inv = 1.0f / l_sum;
+                __nv_bfloat16* dst = a.out + ((size_t)wk.b * a.L + row) * H + wk.h * ATT_DH;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace md
+
+using namespace md;
+
+extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const void* qkv, void* out, int B, int L, int NH, int DH, cudaStream_t stream) {
+    if (DH != ATT_DH) { set_last_error("md_attention_bf16: head dim %d unsupported (kernel is specialised for 64)", DH); return MD_ERR_ARG; }
+    if (B <= 0 || L <= 0 || NH <= 0) { set_last_error("md_attention_bf16: empty problem B=%d L=%d NH=%d", B, L, NH); return MD_ERR_ARG; }
+    const int H = NH * DH;
+    CUtensorMap tm;
+    if (int e = make_tmap_bf16_3d(&tm, qkv, 3 * H, L, B, 3 * H, (uint64_t)L * 3 * H, 64, 128)) return e;
+    AttArgs a;
+    a.B = B; a.L = L; a.NH = NH;
+    a.n_qtiles = (L + ATT_BQ - 1) / ATT_BQ;
+    a.n_pairs = (a.n_qtiles + 1) / 2;
+    a.n_kv = (L + ATT_BKV - 1) / ATT_BKV;
+    a.total_work = B * NH * a.n_pairs;
+    a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
+                       "cudaFuncSetAttribute(attention)"))
+            return MD_ERR_CUDA;
+        attr_set = true;
+    }
+    const int grid = a.total_work < num_sms() ? a.total_work : num_sms();
+    attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm, a);
+    return check_cuda(cudaGetLastError(), "attention launch");
+}

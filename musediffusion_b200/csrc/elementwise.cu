@@ -1,0 +1,553 @@
+// HBM-bound kernels of the sampling path: fused posterior step, q_sample / noise init, LayerNorm, embedding gather,
+// timestep-embedding MLP, casts.  Coalesced 128-bit accesses, warp-shuffle reductions, schedule coefficients in
+// __constant__ memory, counter-based Philox noise generated in-kernel.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "musediff_b200.h"
+
+namespace md {
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return MD_OK;
+    set_last_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return MD_ERR_CUDA;
+}
+int num_sms();
+
+// ----------------------------------------------------------------------------------------------
+// schedule tables
+// ----------------------------------------------------------------------------------------------
+enum { TAB_C1 = 0, TAB_C2, TAB_LOGVAR, TAB_SR, TAB_SRM1, TAB_AB, TAB_ABP, TAB_SQRT_AB, TAB_SQRT_1MAB, TAB_COUNT };
+constexpr int kConstTabs = 7;
+__constant__ float c_sched[kConstTabs * MD_MAX_CONST_T];
+static float* g_sched_dev = nullptr;   // [TAB_COUNT][T] device copy (q_sample tables, and T > MD_MAX_CONST_T)
+static int g_sched_T = 0;
+static int g_sched_cap = 0;
+
+struct SchedRef {
+    const float* dev;  // device table or nullptr -> constant memory
+    int T;
+    MD_DEVINL float get(int tab, int t) const {
+        return dev ? dev[tab * T + t] : c_sched[tab * MD_MAX_CONST_T + t];
+    }
+};
+static SchedRef sched_ref() {
+    SchedRef s;
+    s.T = g_sched_T;
+    s.dev = (g_sched_T <= MD_MAX_CONST_T) ? nullptr : g_sched_dev;
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Philox4x32-10 + inverse-CDF normals
+// ----------------------------------------------------------------------------------------------
+MD_DEVINL uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// Acklam's rational approximation of the standard normal quantile (|rel err| ~1e-9 in exact arithmetic).
+MD_DEVINL float norm_quantile(float p) {
+    const float a0 = -3.969683028665376e+01f, a1 = 2.209460984245205e+02f, a2 = -2.759285104469687e+02f,
+                a3 = 1.383577518672690e+02f, a4 = -3.066479806614716e+01f, a5 = 2.506628277459239e+00f;
+    const float b0 = -5.447609879822406e+01f, b1 = 1.615858368580409e+02f, b2 = -1.556989798598866e+02f,
+                b3 = 6.680131188771972e+01f, b4 = -1.328068155288572e+01f;
+    const float c0 = -7.784894002430293e-03f, c1 = -3.223964580411365e-01f, c2 = -2.400758277161838e+00f,
+                c3 = -2.549732539343734e+00f, c4 = 4.374664141464968e+00f, c5 = 2.938163982698783e+00f;
+    const float d0 = 7.784695709041462e-03f, d1 = 3.224671290700398e-01f, d2 = 2.445134137142996e+00f,
+                d3 = 3.754408661907416e+00f;
+    const float plow = 0.02425f;
+    if (p < plow || p > 1.0f - plow) {
+        const bool upper = p > 0.5f;
+        const float pp = upper ? 1.0f - p : p;
+        const float q = sqrtf(-2.0f * logf(fmaxf(pp, 1e-30f)));
+        const float x = (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) /
+                        ((((d0 * q + d1) * q + d2) * q + d3) * q + 1.0f);
+        return upper ? -x : x;
+    }
+    const float q = p - 0.5f;
+    const float r = q * q;
+    return (((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q /
+           (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1.0f);
+}
+struct NoiseGen {
+    uint2 key;
+    uint32_t step_lo, step_hi;
+    float p_lo, p_span;  // uniform u in (0,1) -> p = p_lo + u * p_span
+    __host__ void init(uint64_t seed, uint64_t step, float top_p) {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        step_lo = (uint32_t)step;
+        step_hi = (uint32_t)(step >> 32);
+        if (top_p > 0.0f) {
+            const double lo = 0.5 * erfc((double)top_p / sqrt(2.0));  // Phi(-top_p)
+            p_lo = (float)lo;
+            p_span = (float)(1.0 - 2.0 * lo);
+        } else {
+            p_lo = 0.0f;
+            p_span = 1.0f;
+        }
+    }
+    // four normals for the aligned group of 4 elements starting at global element index 4*g
+    MD_DEVINL float4 draw4(uint64_t g) const {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), step_lo, step_hi), key);
+        // u = (top 24 bits + 0.5) * 2^-24: exactly representable, strictly inside (0, 1)
+        const float s = 5.9604644775390625e-08f;  // 2^-24
+        float4 n;
+        n.x = norm_quantile(fmaf(fmaf((float)(r.x >> 8), s, 0.5f * s), p_span, p_lo));
+        n.y = norm_quantile(fmaf(fmaf((float)(r.y >> 8), s, 0.5f * s), p_span, p_lo));
+        n.z = norm_quantile(fmaf(fmaf((float)(r.z >> 8), s, 0.5f * s), p_span, p_lo));
+        n.w = norm_quantile(fmaf(fmaf((float)(r.w >> 8), s, 0.5f * s), p_span, p_lo));
+        return n;
+    }
+};
+
+MD_DEVINL float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+MD_DEVINL void st_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// fused posterior step
+// ----------------------------------------------------------------------------------------------
+struct StepArgs {
+    const float* x_t;
+    const int32_t* idx;
+    const float* pred_in;
+    const float* E;
+    const float* noise;
+    const int32_t* t;
+    const int32_t* mask;
+    int64_t mask_tok_stride, mask_d_stride;
+    const float* x_start;
+    float* x_out;
+    __nv_bfloat16* out_bf16;
+    int64_t seq_offset;
+    int B, L, D;
+    float eta;
+    int clip;
+    NoiseGen rng;
+    SchedRef sched;
+};
+
+MD_DEVINL float clampf(float v, int clip) { return clip ? fminf(fmaxf(v, -1.0f), 1.0f) : v; }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
+    const int vec_per_tok = a.D >> 2;
+    const int64_t total = (int64_t)a.B * a.L * vec_per_tok;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tok = i / vec_per_tok;
+        const int d = (int)(i - tok * vec_per_tok) << 2;
+        const int b = (int)(tok / a.L);
+        const int t = a.t[b];
+        const int64_t off = tok * a.D + d;
+        const float4 x = ld_stream_f4(a.x_t + off);
+        float4 pr;
+        if (a.idx != nullptr) pr = *reinterpret_cast<const float4*>(a.E + (int64_t)a.idx[tok] * a.D + d);
+        else pr = ld_stream_f4(a.pred_in + off);
+        pr.x = clampf(pr.x, a.clip); pr.y = clampf(pr.y, a.clip); pr.z = clampf(pr.z, a.clip); pr.w = clampf(pr.w, a.clip);
+        float4 n;
+        if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
+        else n = a.rng.draw4((uint64_t)(((a.seq_offset * a.L) * a.D + off) >> 2));
+        const float nz = (t != 0) ? 1.0f : 0.0f;
+        float4 o;
+        if (MODE == MD_STEP_DDPM) {
+            // mean = c1 * pred + c2 * x ; sample = mean + (nz * exp(0.5 * logvar)) * noise   (no FMA contraction:
+            // same fp32 op sequence as the reference's torch expression)
+            const float c1 = a.sched.get(TAB_C1, t), c2 = a.sched.get(TAB_C2, t);
+            const float sd = __fmul_rn(nz, expf(__fmul_rn(0.5f, a.sched.get(TAB_LOGVAR, t))));
+            o.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.x), __fmul_rn(c2, x.x)), __fmul_rn(sd, n.x));
+            o.y = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.y), __fmul_rn(c2, x.y)), __fmul_rn(sd, n.y));
+            o.z = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.z), __fmul_rn(c2, x.z)), __fmul_rn(sd, n.z));
+            o.w = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.w), __fmul_rn(c2, x.w)), __fmul_rn(sd, n.w));
+        } else {
+            const float sr = a.sched.get(TAB_SR, t), srm1 = a.sched.get(TAB_SRM1, t);
+            const float ab = a.sched.get(TAB_AB, t), abp = a.sched.get(TAB_ABP, t);
+            const float sigma = __fmul_rn(__fmul_rn(a.eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)))),
+                                          __fsqrt_rn(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+            const float ca = __fsqrt_rn(abp);
+            const float cb = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma)));
+            const float sn = __fmul_rn(nz, sigma);
+#define MD_DDIM1(X, P, N) \
+    __fadd_rn(__fadd_rn(__fmul_rn(P, ca), __fmul_rn(cb, __fdiv_rn(__fsub_rn(__fmul_rn(sr, X), P), srm1))), __fmul_rn(sn, N))
+            o.x = MD_DDIM1(x.x, pr.x, n.x);
+            o.y = MD_DDIM1(x.y, pr.y, n.y);
+            o.z = MD_DDIM1(x.z, pr.z, n.z);
+            o.w = MD_DDIM1(x.w, pr.w, n.w);
+#undef MD_DDIM1
+        }
+        if (a.mask != nullptr) {
+            const int32_t* mp = a.mask + tok * a.mask_tok_stride + (int64_t)d * a.mask_d_stride;
+            const float4 xs = *reinterpret_cast<const float4*>(a.x_start + off);
+            const int64_t ds = a.mask_d_stride;
+            if (mp[0] == 0) o.x = xs.x;
+            if (mp[ds] == 0) o.y = xs.y;
+            if (mp[2 * ds] == 0) o.z = xs.z;
+            if (mp[3 * ds] == 0) o.w = xs.w;
+        }
+        st_stream_f4(a.x_out + off, o);
+        if (a.out_bf16 != nullptr)
+            *reinterpret_cast<uint2*>(a.out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+xstart_from_eps_kernel(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D, SchedRef s) {
+    const int vec_per_tok = D >> 2;
+    const int64_t total = (int64_t)B * L * vec_per_tok;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tok = i / vec_per_tok;
+        const int tt = t[tok / L];
+        const float sr = s.get(TAB_SR, tt), srm1 = s.get(TAB_SRM1, tt);
+        const float4 x = ld_stream_f4(x_t + i * 4), e = ld_stream_f4(eps + i * 4);
+        float4 o;
+        o.x = __fsub_rn(__fmul_rn(sr, x.x), __fmul_rn(srm1, e.x));
+        o.y = __fsub_rn(__fmul_rn(sr, x.y), __fmul_rn(srm1, e.y));
+        o.z = __fsub_rn(__fmul_rn(sr, x.z), __fmul_rn(srm1, e.z));
+        o.w = __fsub_rn(__fmul_rn(sr, x.w), __fmul_rn(srm1, e.w));
+        st_stream_f4(out + i * 4, o);
+    }
+}
+
+struct QSampleArgs {
+    const float* x0;
+    const float* noise;
+    const int32_t* t;
+    const int32_t* mask;
+    int64_t mask_tok_stride, mask_d_stride;
+    float* out;
+    __nv_bfloat16* out_bf16;
+    int64_t seq_offset;
+    int B, L, D;
+    NoiseGen rng;
+    const float* sched_dev;
+    int T;
+};
+__global__ void __launch_bounds__(256) q_sample_kernel(const QSampleArgs a) {
+    const int vec_per_tok = a.D >> 2;
+    const int64_t total = (int64_t)a.B * a.L * vec_per_tok;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tok = i / vec_per_tok;
+        const int d = (int)(i - tok * vec_per_tok) << 2;
+        const int64_t off = tok * a.D + d;
+        const int t = a.t ? a.t[tok / a.L] : -1;
+        const float4 x = ld_stream_f4(a.x0 + off);
+        float4 n;
+        if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
+        else n = a.rng.draw4((uint64_t)(((a.seq_offset * a.L) * a.D + off) >> 2));
+        float4 o = n;
+        if (t >= 0) {
+            const float ca = a.sched_dev[TAB_SQRT_AB * a.T + t], cb = a.sched_dev[TAB_SQRT_1MAB * a.T + t];
+            o.x = __fadd_rn(__fmul_rn(ca, x.x), __fmul_rn(cb, n.x));
+            o.y = __fadd_rn(__fmul_rn(ca, x.y), __fmul_rn(cb, n.y));
+            o.z = __fadd_rn(__fmul_rn(ca, x.z), __fmul_rn(cb, n.z));
+            o.w = __fadd_rn(__fmul_rn(ca, x.w), __fmul_rn(cb, n.w));
+        }
+        if (a.mask != nullptr) {
+            const int32_t* mp = a.mask + tok * a.mask_tok_stride + (int64_t)d * a.mask_d_stride;
+            const int64_t ds = a.mask_d_stride;
+            if (mp[0] == 0) o.x = x.x;
+            if (mp[ds] == 0) o.y = x.y;
+            if (mp[2 * ds] == 0) o.z = x.z;
+            if (mp[3 * ds] == 0) o.w = x.w;
+        }
+        st_stream_f4(a.out + off, o);
+        if (a.out_bf16 != nullptr)
+            *reinterpret_cast<uint2*>(a.out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_normal_kernel(float* out, int64_t n, int64_t elem_offset, NoiseGen rng) {
+    const int64_t nv = (n + 3) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = rng.draw4((uint64_t)((elem_offset >> 2) + i));
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 4; ++j)
+            if (i * 4 + j < n) out[i * 4 + j] = vv[j];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// casts / gather
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(in + i * 4);
+        *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256) embed_gather_kernel(const float* E, const IdT* ids, float* out, int64_t M, int V, int D,
+                                                           int* err_flag) {
+    const int vec_per_tok = D >> 2;
+    const int64_t total = M * vec_per_tok;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tok = i / vec_per_tok;
+        const int d = (int)(i - tok * vec_per_tok) << 2;
+        int64_t id = (int64_t)ids[tok];
+        if (id < 0 || id >= V) { if (err_flag) atomicExch(err_flag, 1); id = 0; }
+        st_stream_f4(out + tok * D + d, *reinterpret_cast<const float4*>(E + id * D + d));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm (bf16 in/out, fp32 statistics), one warp per row
+// ----------------------------------------------------------------------------------------------
+template <int VEC>  // VEC 16-byte vectors (8 bf16) per lane: H = 256 * VEC
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        __nv_bfloat16* __restrict__ out, int64_t M) {
+    constexpr int H = 256 * VEC;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp_global; row < M; row += nwarps) {
+        const __nv_bfloat16* p = in + row * H;
+        float v[VEC * 8];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p + (j * 32 + lane) * 8);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float2 f = unpack_bf16x2(w[h]);
+                v[j * 8 + 2 * h] = f.x;
+                v[j * 8 + 2 * h + 1] = f.y;
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC * 8; ++j) s += v[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / H);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC * 8; ++j) { const float dlt = v[j] - mean; q = fmaf(dlt, dlt, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / H) + eps);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int c = (j * 32 + lane) * 8;
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = fmaf((v[j * 8 + e] - mean) * rstd, gg[e], bb[e]);
+            *reinterpret_cast<uint4*>(out + row * H + c) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                                     pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// timestep embedding + time_embed MLP: one block per sequence, fp32, warp-per-output-row dot products
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) timestep_mlp_kernel(const float* __restrict__ t, const float* __restrict__ W0,
+                                                           const float* __restrict__ b0, const float* __restrict__ W2,
+                                                           const float* __restrict__ b2, float* __restrict__ out, int t_dim,
+                                                           int mid_dim, int out_dim) {
+    extern __shared__ float sm[];
+    float* emb = sm;            // [t_dim]
+    float* hid = sm + t_dim;    // [mid_dim]
+    const int b = blockIdx.x;
+    const int half = t_dim / 2;
+    const float tv = t[b];
+    for (int k = threadIdx.x; k < t_dim; k += blockDim.x) {
+        float e = 0.f;
+        if (k < 2 * half) {
+            const int kk = (k < half) ? k : k - half;
+            // freqs = exp(-log(10000) * arange(half) / half) in fp32, args = t * freqs  (network.py:121-125)
+            const float freq = expf(-9.210340371976184f * (float)kk / (float)half);
+            const float arg = tv * freq;
+            e = (k < half) ? cosf(arg) : sinf(arg);
+        }
+        emb[k] = e;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < mid_dim; r += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < t_dim; k += 32) acc = fmaf(W0[(size_t)r * t_dim + k], emb[k], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const float z = acc + b0[r];
+            hid[r] = z / (1.0f + expf(-z));   // SiLU
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < out_dim; r += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < mid_dim; k += 32) acc = fmaf(W2[(size_t)r * mid_dim + k], hid[k], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[(size_t)b * out_dim + r] = acc + b2[r];
+    }
+}
+
+static int ew_grid(int64_t work_items, int threads) {
+    const int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 8;   // 8 resident 256-thread CTAs per SM, grid-stride beyond that
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace md
+
+using namespace md;
+
+extern "C" __attribute__((visibility("default"))) const char* md_last_error(void) { return g_err; }
+extern "C" __attribute__((visibility("default"))) int md_abi_version(void) { return 1; }
+
+extern "C" __attribute__((visibility("default"))) int md_set_schedule(const float* tables, int T, cudaStream_t stream) {
+    if (tables == nullptr || T <= 0) { set_last_error("md_set_schedule: bad arguments (T=%d)", T); return MD_ERR_ARG; }
+    if (T > g_sched_cap) {
+        if (g_sched_dev) cudaFree(g_sched_dev);
+        g_sched_dev = nullptr;
+        if (check_cuda(cudaMalloc(&g_sched_dev, sizeof(float) * TAB_COUNT * T), "cudaMalloc(schedule)")) return MD_ERR_CUDA;
+        g_sched_cap = T;
+    }
+    g_sched_T = T;
+    if (check_cuda(cudaMemcpyAsync(g_sched_dev, tables, sizeof(float) * TAB_COUNT * T, cudaMemcpyHostToDevice, stream),
+                   "cudaMemcpyAsync(schedule)"))
+        return MD_ERR_CUDA;
+    if (T <= MD_MAX_CONST_T) {
+        for (int k = 0; k < kConstTabs; ++k)
+            if (check_cuda(cudaMemcpyToSymbolAsync(c_sched, tables + (size_t)k * T, sizeof(float) * T,
+                                                   sizeof(float) * k * MD_MAX_CONST_T, cudaMemcpyHostToDevice, stream),
+                           "cudaMemcpyToSymbolAsync(schedule)"))
+                return MD_ERR_CUDA;
+    }
+    return check_cuda(cudaStreamSynchronize(stream), "md_set_schedule sync");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_cast_f32_bf16(const float* in, void* out, int64_t n, cudaStream_t stream) {
+    if (n % 4 != 0) { set_last_error("md_cast_f32_bf16: n must be a multiple of 4"); return MD_ERR_ARG; }
+    if (n == 0) return MD_OK;
+    cast_f32_bf16_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4);
+    return check_cuda(cudaGetLastError(), "cast launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out, int64_t M, int V, int D,
+                               cudaStream_t stream) {
+    if (D % 4 != 0) { set_last_error("md_embed_gather: D must be a multiple of 4"); return MD_ERR_ARG; }
+    if (M == 0) return MD_OK;
+    const int grid = ew_grid(M * (D / 4), 256);
+    if (ids_is_i64) embed_gather_kernel<int64_t><<<grid, 256, 0, stream>>>(E, (const int64_t*)ids, out, M, V, D, nullptr);
+    else embed_gather_kernel<int32_t><<<grid, 256, 0, stream>>>(E, (const int32_t*)ids, out, M, V, D, nullptr);
+    return check_cuda(cudaGetLastError(), "embed_gather launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_timestep_mlp(const float* t, const float* W0, const float* b0, const float* W2, const float* b2,
+                               float* out, int B, int t_dim, int mid_dim, int out_dim, cudaStream_t stream) {
+    if (B <= 0) return MD_OK;
+    const size_t smem = sizeof(float) * (t_dim + mid_dim);
+    timestep_mlp_kernel<<<B, 256, smem, stream>>>(t, W0, b0, W2, b2, out, t_dim, mid_dim, out_dim);
+    return check_cuda(cudaGetLastError(), "timestep_mlp launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const void* in, const float* gamma, const float* beta, float eps, void* out, int64_t M,
+                                 int H, cudaStream_t stream) {
+    if (H % 256 != 0 || H > 2048 || H <= 0) { set_last_error("md_layernorm_bf16: H=%d must be a multiple of 256, <= 2048", H); return MD_ERR_ARG; }
+    if (M == 0) return MD_OK;
+    const int grid = ew_grid(M * 32, 256);
+    const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    switch (H / 256) {
+        case 1: layernorm_kernel<1><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 2: layernorm_kernel<2><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 3: layernorm_kernel<3><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 4: layernorm_kernel<4><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 5: layernorm_kernel<5><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 6: layernorm_kernel<6><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 7: layernorm_kernel<7><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        default: layernorm_kernel<8><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+    }
+    return check_cuda(cudaGetLastError(), "layernorm launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_posterior_step(const float* x_t, const int32_t* idx, const float* pred_in, const float* E,
+                                 const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
+                                 const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride,
+                                 const float* x_start, float* x_out, void* out_bf16, int B, int L, int D, int mode,
+                                 float eta, int clip, float top_p, cudaStream_t stream) {
+    if (g_sched_T == 0) { set_last_error("md_posterior_step: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (D % 4 != 0) { set_last_error("md_posterior_step: D must be a multiple of 4"); return MD_ERR_ARG; }
+    if ((idx == nullptr) == (pred_in == nullptr)) { set_last_error("md_posterior_step: exactly one of idx / pred_in"); return MD_ERR_ARG; }
+    if (idx != nullptr && E == nullptr) { set_last_error("md_posterior_step: idx needs E"); return MD_ERR_ARG; }
+    if (mask != nullptr && x_start == nullptr) { set_last_error("md_posterior_step: mask needs x_start"); return MD_ERR_ARG; }
+    if (mode != MD_STEP_DDPM && mode != MD_STEP_DDIM) { set_last_error("md_posterior_step: bad mode %d", mode); return MD_ERR_ARG; }
+    if ((int64_t)B * L == 0) return MD_OK;
+    StepArgs a;
+    a.x_t = x_t; a.idx = idx; a.pred_in = pred_in; a.E = E; a.noise = noise; a.t = t; a.mask = mask;
+    a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride; a.x_start = x_start; a.x_out = x_out;
+    a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
+    a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref();
+    const int grid = ew_grid((int64_t)B * L * (D / 4), 256);
+    if (mode == MD_STEP_DDPM) posterior_step_kernel<MD_STEP_DDPM><<<grid, 256, 0, stream>>>(a);
+    else posterior_step_kernel<MD_STEP_DDIM><<<grid, 256, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "posterior_step launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D,
+                                  cudaStream_t stream) {
+    if (g_sched_T == 0) { set_last_error("md_xstart_from_eps: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (D % 4 != 0) { set_last_error("md_xstart_from_eps: D must be a multiple of 4"); return MD_ERR_ARG; }
+    if ((int64_t)B * L == 0) return MD_OK;
+    xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, out, B, L, D, sched_ref());
+    return check_cuda(cudaGetLastError(), "xstart_from_eps launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
+                           const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride,
+                           float* out, void* out_bf16, int B, int L, int D, cudaStream_t stream) {
+    if (t != nullptr && g_sched_T == 0) { set_last_error("md_q_sample: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (D % 4 != 0) { set_last_error("md_q_sample: D must be a multiple of 4"); return MD_ERR_ARG; }
+    if ((int64_t)B * L == 0) return MD_OK;
+    QSampleArgs a;
+    a.x0 = x0; a.noise = noise; a.t = t; a.mask = mask; a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride;
+    a.out = out; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
+    a.rng.init(seed, step_counter, 0.0f); a.sched_dev = g_sched_dev; a.T = g_sched_T;
+    q_sample_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "q_sample launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t step_counter, int64_t elem_offset, float top_p,
+                              cudaStream_t stream) {
+    if (elem_offset % 4 != 0) { set_last_error("md_fill_normal: elem_offset must be a multiple of 4"); return MD_ERR_ARG; }
+    if (n == 0) return MD_OK;
+    NoiseGen g;
+    g.init(seed, step_counter, top_p);
+    fill_normal_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, stream>>>(out, n, elem_offset, g);
+    return check_cuda(cudaGetLastError(), "fill_normal launch");
+}

@@ -1,0 +1,369 @@
+// Persistent warp-specialised tcgen05 GEMM for the denoiser's Linear layers (sm_100a).
+//
+//   out[M, N] = epilogue( A[M, K] (bf16, row-major)  x  W[N, K]^T (bf16, nn.Linear layout)  + bias[N] )
+//
+// Replaces every nn.Linear of TransformerNetModel.forward (reference MuseDiffusion/models/network.py:139-154 and
+// the HF BertLayer linears called from network.py:151).  Both operands are K-major, so TMA (SWIZZLE_128B boxes of
+// 64 bf16) feeds tcgen05.mma directly; fp32 accumulators live in TMEM (2 stages x BN columns) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> bias / GELU / tanh / residual / pos+time -> global).
+#include "common.cuh"
+#include "musediff_b200.h"
+
+namespace md {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiThreads = 256;
+
+struct GemmArgs {
+    int M, N, K;
+    int L;                         // rows per sequence (EPI_POS_TIME)
+    const float* bias;             // [N] or nullptr
+    const __nv_bfloat16* resid;    // [M, N]   (MD_EPI_BIAS_RESID)
+    const float* pos;              // [L, N]   (MD_EPI_BIAS_POS_TIME)
+    const float* temb;             // [M / L, N] (row stride temb_stride; 0 = one row shared by all sequences)
+    int temb_stride;
+    void* out;                     // bf16 or fp32 [M, N]
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+};
+
+template <int EPI>
+MD_DEVINL float epi_act(float v) {
+    if (EPI == MD_EPI_BIAS_GELU) return gelu_erf(v);
+    if (EPI == MD_EPI_BIAS_TANH) return fast_tanh(v);
+    return v;
+}
+
+template <int BN, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
+    float* sBias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::kStages;
+    uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const int num_tiles = n_tiles * m_tiles;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], kEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+                    const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // +32 bytes per UMMA_K step inside the 128B swizzle atom  (encoded >> 4)
+                        umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 2;
+        const int q = warp & 3;             // TMEM lane quadrant this warp may access
+        const int hsel = ew >> 2;           // which half of the BN columns
+        const int tid_e = threadIdx.x - 64;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        constexpr int kChunks = BN / 2 / 32;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int n0 = n_blk * BN;
+            if (tid_e < BN) {
+                const int n = n0 + tid_e;
+                sBias[acc * BN + tid_e] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.0f;
+            }
+            named_bar_sync(1, kEpiThreads);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const size_t row_off = (size_t)row * p.N;
+            int seq_b = 0, seq_l = 0;
+            if (EPI == MD_EPI_BIAS_POS_TIME && row_ok) { seq_b = row / p.L; seq_l = row - seq_b * p.L; }
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                const int col0 = hsel * (BN / 2) + c * 32;
+                const int n = n0 + col0;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0, r);
+                uint4 res[4];
+                if (EPI == MD_EPI_BIAS_RESID) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        res[g] = make_uint4(0, 0, 0, 0);
+                        if (row_ok && n + g * 8 < p.N)
+                            res[g] = *reinterpret_cast<const uint4*>(p.resid + row_off + n + g * 8);
+                    }
+                }
+                tc_wait_ld();
+                float v[32];
+                const float* bias_s = sBias + acc * BN + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[j];
+                if (EPI == MD_EPI_BIAS_RESID) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t w[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 f = unpack_bf16x2(w[h]);
+                            v[g * 8 + 2 * h] += f.x;
+                            v[g * 8 + 2 * h + 1] += f.y;
+                        }
+                    }
+                }
+                if (EPI == MD_EPI_BIAS_POS_TIME) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            if (n + g * 4 < p.N) {
+                                const float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)seq_l * p.N + n + g * 4);
+                                const float4 b = *reinterpret_cast<const float4*>(p.temb + (size_t)seq_b * p.temb_stride + n + g * 4);
+                                v[g * 4 + 0] += a.x + b.x;
+                                v[g * 4 + 1] += a.y + b.y;
+                                v[g * 4 + 2] += a.z + b.z;
+                                v[g * 4 + 3] += a.w + b.w;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = epi_act<EPI>(v[j]);
+                if (row_ok) {
+                    if (OUT_F32) {
+                        float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (n + g * 4 < p.N)
+                                *reinterpret_cast<float4*>(o + g * 4) =
+                                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (n + g * 8 < p.N)
+                                *reinterpret_cast<uint4*>(o + g * 8) =
+                                    make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                               pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%llu cols=%llu stride=%llu box=%ux%u base=%p)", (int)r,
+                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows,
+                       box_cols, base);
+        return MD_ERR_CUDA;
+    }
+    return MD_OK;
+}
+
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous), box = [1, box1, box0], 128B swizzle; rows beyond d1 read as zero.
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                      uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstr[2] = {stride1_elems * 2, stride2_elems * 2};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d (dims=%llu,%llu,%llu base=%p)", (int)r,
+                       (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, base);
+        return MD_ERR_CUDA;
+    }
+    return MD_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int EPI, bool OUT_F32>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_kernel<BN, EPI, OUT_F32>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+                       "cudaFuncSetAttribute(gemm)"))
+            return MD_ERR_CUDA;
+        attr_set = true;
+    }
+    const int n_tiles = (args.N + BN - 1) / BN, m_tiles = (args.M + BM - 1) / BM;
+    const int grid = min(n_tiles * m_tiles, num_sms());
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+    return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+template <int BN, bool OUT_F32>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t s) {
+    switch (epi) {
+        case MD_EPI_BIAS: return launch_gemm<BN, MD_EPI_BIAS, OUT_F32>(tmA, tmB, a, s);
+        case MD_EPI_BIAS_GELU: return launch_gemm<BN, MD_EPI_BIAS_GELU, OUT_F32>(tmA, tmB, a, s);
+        case MD_EPI_BIAS_TANH: return launch_gemm<BN, MD_EPI_BIAS_TANH, OUT_F32>(tmA, tmB, a, s);
+        case MD_EPI_BIAS_RESID: return launch_gemm<BN, MD_EPI_BIAS_RESID, OUT_F32>(tmA, tmB, a, s);
+        case MD_EPI_BIAS_POS_TIME: return launch_gemm<BN, MD_EPI_BIAS_POS_TIME, OUT_F32>(tmA, tmB, a, s);
+    }
+    set_last_error("md_linear_bf16: unknown epilogue %d", epi);
+    return MD_ERR_ARG;
+}
+
+}  // namespace md
+
+using namespace md;
+
+extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epilogue,
+                              int out_is_f32, const void* resid, const float* pos, const float* temb, int temb_stride,
+                              int L, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0) { set_last_error("md_linear_bf16: empty problem M=%d N=%d K=%d", M, N, K); return MD_ERR_ARG; }
+    if (K % 8 != 0 || N % 8 != 0) { set_last_error("md_linear_bf16: K and N must be multiples of 8 (K=%d N=%d)", K, N); return MD_ERR_ARG; }
+    if (epilogue == MD_EPI_BIAS_RESID && resid == nullptr) { set_last_error("md_linear_bf16: residual pointer missing"); return MD_ERR_ARG; }
+    if (epilogue == MD_EPI_BIAS_POS_TIME && (pos == nullptr || temb == nullptr || L <= 0 || M % L != 0)) {
+        set_last_error("md_linear_bf16: pos/time epilogue needs pos, temb and L dividing M");
+        return MD_ERR_ARG;
+    }
+    const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_bf16_2d(&tmA, A, M, K, K, BM, BK)) return e;
+    if (int e = make_tmap_bf16_2d(&tmB, W, N, K, K, BN, BK)) return e;
+    GemmArgs a;
+    a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
+    a.bias = bias; a.resid = reinterpret_cast<const __nv_bfloat16*>(resid); a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
+    if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, a, stream)
+                                     : dispatch_epi<256, false>(epilogue, tmA, tmB, a, stream);
+    return out_is_f32 ? dispatch_epi<128, true>(epilogue, tmA, tmB, a, stream)
+                      : dispatch_epi<128, false>(epilogue, tmA, tmB, a, stream);
+}

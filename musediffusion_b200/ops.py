@@ -1,0 +1,201 @@
+"""Tensor-level wrappers over the C-ABI kernels, plus their registration as `torch.ops.musediff_b200.*` custom ops.
+
+Every function here launches hand-written sm_100a kernels on the current CUDA stream; inputs must be CUDA tensors
+(a CPU tensor raises — there is no fallback)."""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MuseDiffLibraryError("musediffusion_b200 ops need CUDA tensors (got a %s tensor)" % t.device)
+    return t.data_ptr()
+
+
+def _c(t, dtype=None):
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ schedule
+TABLE_ORDER = ["posterior_mean_coef1", "posterior_mean_coef2", "model_log_variance", "sqrt_recip_alphas_cumprod",
+               "sqrt_recipm1_alphas_cumprod", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+               "sqrt_one_minus_alphas_cumprod"]
+_current_schedule_key = [None]
+
+
+def set_schedule(tables64, key=None):
+    """tables64: dict name -> float64 numpy [T].  Cast to fp32 exactly like _extract_into_tensor
+    (MuseDiffusion/models/diffusion.py:914) and uploaded once; `key` lets callers skip redundant uploads."""
+    if key is not None and _current_schedule_key[0] == key:
+        return
+    T = len(tables64[TABLE_ORDER[0]])
+    host = np.ascontiguousarray(np.stack([np.asarray(tables64[n], dtype=np.float64).astype(np.float32)
+                                          for n in TABLE_ORDER]))
+    call("md_set_schedule", host.ctypes.data, T, _stream())
+    _current_schedule_key[0] = key
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def cast_bf16(x):
+    x = _c(x, torch.float32)
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    call("md_cast_f32_bf16", _p(x), _p(out), x.numel(), _stream())
+    return out
+
+
+def embed_gather(E, ids):
+    E = _c(E, torch.float32)
+    if ids.dtype not in (torch.int32, torch.int64):
+        ids = ids.to(torch.int64)
+    ids = _c(ids)
+    out = torch.empty(tuple(ids.shape) + (E.shape[1],), dtype=torch.float32, device=E.device)
+    call("md_embed_gather", _p(E), _p(ids), int(ids.dtype == torch.int64), _p(out), ids.numel(), E.shape[0],
+         E.shape[1], _stream())
+    return out
+
+
+def timestep_mlp(t, W0, b0, W2, b2):
+    t = _c(t, torch.float32)
+    out = torch.empty((t.numel(), W2.shape[0]), dtype=torch.float32, device=t.device)
+    call("md_timestep_mlp", _p(t), _p(W0), _p(b0), _p(W2), _p(b2), _p(out), t.numel(), W0.shape[1], W0.shape[0],
+         W2.shape[0], _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None):
+    assert x.dtype == BF16 and x.is_contiguous()
+    H = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    call("md_layernorm_bf16", _p(x), _p(gamma), _p(beta), float(eps), _p(out), x.numel() // H, H, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ contractions
+def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, resid=None, pos=None, temb=None, temb_stride=0, L=0,
+           out=None):
+    """out[M,N] = epi(A[M,K] @ W[N,K]^T + bias)."""
+    assert A.dtype == BF16 and W.dtype == BF16 and A.is_contiguous() and W.is_contiguous()
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    call("md_linear_bf16", _p(A), _p(W), _p(bias), _p(out), M, N, K, epilogue, int(out.dtype == torch.float32),
+         _p(resid), _p(pos), _p(temb), temb_stride, L, _stream())
+    return out
+
+
+def attention(qkv, B, L, NH, out=None):
+    assert qkv.dtype == BF16 and qkv.is_contiguous()
+    H = qkv.shape[-1] // 3
+    if out is None:
+        out = torch.empty((B * L, H), dtype=BF16, device=qkv.device)
+    call("md_attention_bf16", _p(qkv), _p(out), B, L, NH, H // NH, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ rounding / decode
+def round_argmin(x, E, want_margin=False):
+    x = _c(x, torch.float32)
+    E = _c(E, torch.float32)
+    D = E.shape[1]
+    M = x.numel() // D
+    idx = torch.empty((M,), dtype=torch.int32, device=x.device)
+    margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
+    call("md_round_argmin", _p(x), _p(E), _p(idx), _p(margin), M, E.shape[0], D, _stream())
+    return (idx, margin) if want_margin else idx
+
+
+def logits_argmax(x, E, bias, want_margin=False):
+    x = _c(x, torch.float32)
+    E = _c(E, torch.float32)
+    bias = _c(bias, torch.float32)
+    D = E.shape[1]
+    M = x.numel() // D
+    tok = torch.empty((M,), dtype=torch.int32, device=x.device)
+    margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
+    call("md_logits_argmax", _p(x), _p(E), _p(bias), _p(tok), _p(margin), M, E.shape[0], D, _stream())
+    return (tok, margin) if want_margin else tok
+
+
+# ------------------------------------------------------------------------------------------------ posterior step
+def _mask_args(mask, B, L, D):
+    """mask: None, or an int tensor broadcastable to [B, L, D] (the reference passes a stride-0 expand of [B, L, 1])."""
+    if mask is None:
+        return None, None, 0, 0
+    if mask.dim() == 2:
+        mask = mask.unsqueeze(-1)
+    m = torch.broadcast_to(mask, (B, L, D))
+    if m.stride(-1) == 0 or D == 1:
+        tok = m[..., 0]
+        tok = tok.to(torch.int32) if tok.dtype != torch.int32 else tok
+        tok = tok.contiguous()
+        return tok, tok, 1, 0
+    full = m.to(torch.int32).contiguous()
+    return full, full, D, 1
+
+
+def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0, step_counter=0, seq_offset=0,
+                   mask=None, x_start=None, eta=0.0, clip=True, top_p=0.0, out=None, out_bf16=None):
+    x_t = _c(x_t, torch.float32)
+    B, L, D = x_t.shape
+    t = _c(t, torch.int32)
+    keep, mask_t, ts, ds = _mask_args(mask, B, L, D)
+    if out is None:
+        out = torch.empty_like(x_t)
+    if pred is not None:
+        pred = _c(pred, torch.float32)
+    if noise is not None:
+        noise = _c(noise, torch.float32)
+    if x_start is not None:
+        x_start = _c(x_start, torch.float32)
+    if idx is not None:
+        idx = _c(idx, torch.int32)
+    call("md_posterior_step", _p(x_t), _p(idx), _p(pred), _p(E), _p(noise), int(seed), int(step_counter),
+         int(seq_offset), _p(t), _p(mask_t), ts, ds, _p(x_start), _p(out), _p(out_bf16), B, L, D, mode, float(eta),
+         int(bool(clip)), float(top_p or 0.0), _stream())
+    return out
+
+
+def xstart_from_eps(x_t, eps, t):
+    x_t = _c(x_t, torch.float32)
+    eps = _c(eps, torch.float32)
+    B, L, D = x_t.shape
+    out = torch.empty_like(x_t)
+    call("md_xstart_from_eps", _p(x_t), _p(eps), _p(_c(t, torch.int32)), _p(out), B, L, D, _stream())
+    return out
+
+
+def q_sample(x0, t=None, noise=None, seed=0, step_counter=0, seq_offset=0, mask=None, out_bf16=None):
+    """t=None -> pure-noise initialisation (generation mode)."""
+    x0 = _c(x0, torch.float32)
+    B, L, D = x0.shape
+    keep, mask_t, ts, ds = _mask_args(mask, B, L, D)
+    out = torch.empty_like(x0)
+    if noise is not None:
+        noise = _c(noise, torch.float32)
+    tt = _c(t, torch.int32) if t is not None else None
+    call("md_q_sample", _p(x0), _p(noise), int(seed), int(step_counter), int(seq_offset), _p(tt), _p(mask_t), ts, ds,
+         _p(out), _p(out_bf16), B, L, D, _stream())
+    return out
+
+
+def fill_normal(shape, device, seed=0, step_counter=0, elem_offset=0, top_p=0.0):
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    call("md_fill_normal", _p(out), out.numel(), int(seed), int(step_counter), int(elem_offset), float(top_p),
+         _stream())
+    return out
