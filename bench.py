@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native MuseDiffusion sampling path (BASELINE.json metric: sequences/sec of full
+reverse-diffusion sampling; ms per denoiser step).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W    the reference algorithm's CPU port (numpy oracle) on host cores
+
+Workload (config 2 of BASELINE.json): base TransformerNetModel (bert-base encoder, seq_len 2096, hidden_dim 128,
+vocab 729), random-init weights, synthetic ComMU-shaped modification batch, 256 sequences per GPU, DDPM chain of
+2000 steps with rounding every step (top_p = 1 truncated noise), bf16 denoiser, fp32 state.
+A bench "step" = ONE reverse-diffusion step of the chain over the whole batch (denoiser forward + nearest-embedding
+rounding + fused posterior update) — every step of the chain launches the same kernels on the same shapes, so
+`value` = sequences / (ms_per_step * 2000 + decode) is the full-chain throughput extrapolated from K consecutive
+chain steps starting at t = 1999 (`--full-chain` runs all 2000 instead).  `e2e` is measured through the public API
+(`sample_batch`: pinned host token ids in, decoded token ids out to host) running K chain steps via the reference's
+own `t_enc` argument, host<->device copies inside the timed region, scaled the same way."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIFFUSION_STEPS = 2000
+L, D, V, H, F, NL, NH = 2096, 128, 729, 768, 3072, 12, 12
+
+
+def flops_per_sequence_step():
+    """L * [2(2DH + 2H^2) + NL(8H^2 + 4HF + 4LH) + 2VD]."""
+    return L * (2 * (2 * D * H + 2 * H * H) + NL * (8 * H * H + 4 * H * F + 4 * L * H) + 2 * V * D)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference algorithm on the host CPU: the numpy port under oracle/ (the reference itself is Python and does
+    not travel to the GPU box).  Each step = one reverse step of the same chain on a bounded
+    sample of the workload (args.ref_batch sequences of the same shape)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import musediff_oracle as O
+    B = args.ref_batch
+    p = O.make_random_params(seed=0, seq_len=L)
+    s = O.make_schedule("sqrt", DIFFUSION_STEPS)
+    cond = O.make_synthetic_batch("modification", B, L, seed=105)
+    x_start = O.get_embeds(p, cond["input_ids"])
+    mask = np.broadcast_to(cond["input_mask"][..., None], x_start.shape)
+    noise = O.NoiseStream(105)
+    x = O.q_sample(s, x_start, np.full((B,), DIFFUSION_STEPS - 1), noise.randn(x_start.shape), mask)
+    E = p["word_embedding.weight"]
+    times = []
+    for k in range(args.warmup + args.steps):
+        i = DIFFUSION_STEPS - 1 - k
+        t = np.full((B,), i, dtype=np.int64)
+        tic = time.perf_counter()
+        mo = O.denoiser_forward(p, x, s.model_timestep(t))
+        x = O.p_sample_step(s, x, t, mo, noise.truncated(x.shape, 1), E, True, mask, x_start)["sample"]
+        times.append(time.perf_counter() - tic)
+    tic = time.perf_counter()
+    O.logits_argmax(p, x)
+    t_dec = time.perf_counter() - tic
+    ms = 1e3 * sum(times[args.warmup:]) / args.steps
+    value = B / (ms * 1e-3 * DIFFUSION_STEPS + t_dec)
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "sequences/sec full reverse-diffusion sampling", "value": value,
+            "unit": "sequences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(B, 1, note="CPU port of the reference algorithm (numpy, host BLAS threads)"),
+            "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": "port",
+                             "sample": "%d sequences x %d consecutive chain steps of the same workload, fp32 numpy "
+                                       "(oracle/musediff_oracle.py), extrapolated to the 2000-step chain" % (B, args.steps)},
+            "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(batch_per_gpu, n_gpus, note=None):
+    c = {"workload": "BASELINE.json configs[1]: base TransformerNetModel (bert-base encoder 12x768, seq_len 2096, "
+                     "hidden_dim 128, vocab 729) random-init; modification (seq2seq) sampling, DDPM 2000 steps, "
+                     "rounding every step, top_p=1; batch %d sequences per GPU" % batch_per_gpu,
+         "global_batch": batch_per_gpu * n_gpus, "seq_len": L, "chain_steps": DIFFUSION_STEPS,
+         "parallelism": "dp%d (batch sharded by sequence, replicated weights, no collective in the loop)" % n_gpus,
+         "step_definition": "one reverse-diffusion step over the whole batch; value extrapolated to the full chain",
+         "l2_policy": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    from musediffusion_b200 import _lib, dist, ops
+    from musediffusion_b200.initialization import create_model_and_diffusion, seed_all
+    from musediffusion_b200.rounding import denoised_fn_round
+    from musediffusion_b200.sample import build_model_emb, sample_batch
+    from musediffusion_b200.synthetic import make_synthetic_batch
+    from functools import partial
+
+    rank, world, dev = dist.setup()
+    B = args.batch
+    targs = SimpleNamespace(hidden_dim=D, hidden_t_dim=128, vocab_size=V, seq_len=L, dropout=0.1, noise_schedule="sqrt",
+                            diffusion_steps=DIFFUSION_STEPS, timestep_respacing="", rescale_timesteps=True,
+                            predict_xstart=True)
+    torch.manual_seed(0)
+    model, diffusion = create_model_and_diffusion(targs)
+    model.eval().requires_grad_(False).to(dev)
+    dist.broadcast_model(model)                                   # NCCL: replicated weights (one-time)
+    model_emb = build_model_emb(model, dev)
+    seed_all(105, deterministic=True)
+    diffusion.seq_offset = rank * B
+    cond_np = make_synthetic_batch("modification", B, L, seed=105 + rank)
+    cond_host = {k: torch.from_numpy(v).pin_memory() for k, v in cond_np.items() if k != "length"}
+    fn = partial(denoised_fn_round, model_emb, dist=None)
+
+    # ---- device-resident timed region: K consecutive chain steps through the loop generator
+    ids = cond_host["input_ids"].to(dev)
+    mask_ori = cond_host["input_mask"].to(dev)
+    x_start = model.get_embeds(ids)
+    mask = torch.broadcast_to(mask_ori.unsqueeze(-1), x_start.shape)
+    x_noised = diffusion.q_sample(x_start.unsqueeze(-1), torch.full((B, 1), DIFFUSION_STEPS - 1, device=dev),
+                                  mask=mask).squeeze(-1)
+    n_total = DIFFUSION_STEPS if args.full_chain else args.warmup + args.steps
+    gen = diffusion._loop(_lib.STEP_DDPM, model, tuple(x_start.shape), x_noised, True, fn, None, dev, False, 1, 0, True,
+                          mask, x_start, 0.0, list(range(DIFFUSION_STEPS))[::-1][:n_total], want_aux=False)
+    sampler = ClockSampler(dev.index or 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    last = None
+    launches0 = 0
+    timed_steps = n_total - args.warmup
+    for k in range(n_total):
+        if k == args.warmup:
+            dist.barrier()
+            torch.cuda.synchronize()
+            sampler.start()
+            launches0 = ops.launch_count()
+            ev0.record()
+        last = next(gen)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = ops.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    # final decode (get_logits + argmax fused), once per batch
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    tokens = model.decode_tokens(last[0])
+    d1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    ms_decode = d0.elapsed_time(d1)
+    t = torch.tensor([ms_total, ms_decode], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total, ms_decode = float(t[0]), float(t[1])
+    ms_step = ms_total / timed_steps
+    value = (B * world) / ((ms_step * DIFFUSION_STEPS + ms_decode) * 1e-3)
+
+    # ---- per-kernel breakdown of one step (CUDA events around every launch), dominant-kernel roofline
+    peaks = load_peaks()
+    prof = ops.profile_step(lambda: next(gen)) if not args.full_chain and not args.no_breakdown else None
+    roofline, breakdown = None, None
+    if prof:
+        breakdown = summarize_profile(prof, B)
+        top = max((v for v in breakdown.values() if v["flops"] > 0), key=lambda v: v["ms"])
+        ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
+                    "launches_per_step": top["launches"], "ms_per_step": top["ms"]}
+    step_tflops = flops_per_sequence_step() * B / (ms_step * 1e-3) / 1e12
+
+    # ---- end to end through the public API: pinned host ids -> tokens on host, K chain steps via t_enc
+    e2e = None
+    if not args.full_chain and not args.no_e2e:
+        k_e2e = args.steps
+        strength = k_e2e / DIFFUSION_STEPS
+        for it in range(2):                                        # first pass = warm-up
+            dist.barrier()
+            torch.cuda.synchronize()
+            tic = time.perf_counter()
+            tok = sample_batch(model, diffusion, model_emb, cond_host, "modification", DIFFUSION_STEPS, DIFFUSION_STEPS,
+                               strength=strength, top_p=1, clamp_step=0, device=dev)
+            tok_host = tok.to("cpu", non_blocking=False)
+            torch.cuda.synchronize()
+            t_e2e = time.perf_counter() - tic
+        te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+        t_e2e = float(te[0])
+        e2e = {"value": (B * world) / (t_e2e * DIFFUSION_STEPS / k_e2e), "unit": "sequences/s",
+               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in cond_host.values())),
+               "d2h_bytes_per_step": int(tok_host.numel() * tok_host.element_size()),
+               "note": "sample_batch() public API, %d chain steps via t_enc incl. H2D ids/mask, embedding gather, "
+                       "q_sample, decode and D2H tokens; whole call scaled by 2000/%d" % (k_e2e, k_e2e),
+               "seconds_per_call": t_e2e}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_sample()
+
+    if rank == 0:
+        line = {"metric": "sequences/sec full reverse-diffusion sampling", "value": value, "unit": "sequences/s",
+                "n_gpus": world, "steps": timed_steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(B, world), "ms_per_denoiser_step": ms_step, "ms_decode": ms_decode,
+                "step_tflops": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
+                "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "kernels": breakdown}
+        print(json.dumps(line))
+    dist.barrier()
+
+
+def summarize_profile(prof, B):
+    """prof: list of (kernel name, detail, ms).  FLOPs: linear 2MNK, attention 4 B NH L^2 64."""
+    out = {}
+    for name, detail, ms in prof:
+        key = name + (":" + detail if detail else "")
+        e = out.setdefault(key, {"name": key, "ms": 0.0, "launches": 0, "flops": 0.0})
+        e["ms"] += ms
+        e["launches"] += 1
+        if name == "md_linear_bf16":
+            M, N, K = [int(v) for v in detail.split(" ")[0].split("x")]
+            e["flops"] += 2.0 * M * N * K
+        elif name == "md_attention_bf16":
+            e["flops"] += 4.0 * B * NH * L * L * 64
+    for e in out.values():
+        if e["flops"]:
+            e["tflops"] = e["flops"] / (e["ms"] * 1e-3) / 1e12
+    return out
+
+
+def cpu_baseline_sample():
+    """bounded CPU sample of the same workload with the oracle port: 1 sequence x 2 chain steps (~15-25 s)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import musediff_oracle as O
+    Bc, steps = 1, 2
+    p = O.make_random_params(seed=0, seq_len=L)
+    s = O.make_schedule("sqrt", DIFFUSION_STEPS)
+    cond = O.make_synthetic_batch("modification", Bc, L, seed=105)
+    x_start = O.get_embeds(p, cond["input_ids"])
+    mask = np.broadcast_to(cond["input_mask"][..., None], x_start.shape)
+    noise = O.NoiseStream(105)
+    x = O.q_sample(s, x_start, np.full((Bc,), DIFFUSION_STEPS - 1), noise.randn(x_start.shape), mask)
+    tic = time.perf_counter()
+    for k in range(steps):
+        t = np.full((Bc,), DIFFUSION_STEPS - 1 - k, dtype=np.int64)
+        mo = O.denoiser_forward(p, x, s.model_timestep(t))
+        x = O.p_sample_step(s, x, t, mo, noise.truncated(x.shape, 1), p["word_embedding.weight"], True, mask, x_start)["sample"]
+    per_step = (time.perf_counter() - tic) / steps
+    return {"value": Bc / (per_step * DIFFUSION_STEPS), "unit": "sequences/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d sequence x %d consecutive chain steps (fp32 numpy oracle, %.2f s/step), extrapolated to 2000 steps"
+                      % (Bc, steps, per_step)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
+    ap.add_argument("--ref-batch", type=int, default=1, help="sequences per step for --impl reference")
+    ap.add_argument("--full-chain", action="store_true", help="run all 2000 chain steps instead of extrapolating")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

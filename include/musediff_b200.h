@@ -97,21 +97,24 @@ int md_logits_argmax(const float* x, const float* E, const float* bias, int32_t*
  *   x'   = mask == 0 ? x_start : x'                     (diffusion.py:394-397, 752-755)
  * n = noise[m, d] if noise != NULL, else a counter-based Philox4x32-10 normal keyed by (seed, step_counter, global
  * element index (seq_offset*L + m)*D + d), truncated to |n| <= top_p by inverse-CDF when top_p > 0 (the law the
- * reference's rejection loop :378-385 samples).  t: int32 [B] schedule index per sequence.  mask: int32, indexed
- * m*mask_tok_stride + d*mask_d_stride (NULL = no mask).  out_bf16 (optional) receives a bf16 copy of x'. */
+ * reference's rejection loop :378-385 samples).  t: int32 schedule index, t[b * t_stride] (t_stride 1 = per sequence,
+ * 0 = one value for the batch, as inside the loops :516,887).  mask: int32, indexed m*mask_tok_stride + d*mask_d_stride
+ * (NULL = no mask).  Optional outputs: out_bf16 = bf16 copy of x' (next step's GEMM operand), pred_out = processed
+ * pred_xstart, mean_out = the mean before noise ("greedy_mean" of p_sample). */
 int md_posterior_step(const float* x_t, const int32_t* idx, const float* pred_in, const float* E, const float* noise,
-                      uint64_t seed, uint64_t step_counter, int64_t seq_offset, const int32_t* t, const int32_t* mask,
-                      int64_t mask_tok_stride, int64_t mask_d_stride, const float* x_start, float* x_out, void* out_bf16,
-                      int B, int L, int D, int mode, float eta, int clip, float top_p, cudaStream_t stream);
+                      uint64_t seed, uint64_t step_counter, int64_t seq_offset, const int32_t* t, int t_stride,
+                      const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride, const float* x_start,
+                      float* x_out, void* out_bf16, float* pred_out, float* mean_out, int B, int L, int D, int mode,
+                      float eta, int clip, float top_p, cudaStream_t stream);
 /* x0 = sqrt_recip[t] x_t - sqrt_recipm1[t] eps  (_predict_xstart_from_eps, diffusion.py:194-199), for
  * predict_xstart = False models. */
-int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D,
-                       cudaStream_t stream);
+int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L,
+                       int D, cudaStream_t stream);
 /* q_sample (diffusion.py:229-255): out = mask==0 ? x0 : sqrt_ab[t] x0 + sqrt_1m_ab[t] n.  t < 0 means "pure
  * noise": out = mask==0 ? x0 : n (the generation-mode initialisation, run/sample.py:190-193).  Noise as above. */
 int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
-                const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride, float* out,
-                void* out_bf16, int B, int L, int D, cudaStream_t stream);
+                const int32_t* t, int t_stride, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride,
+                float* out, void* out_bf16, int B, int L, int D, cudaStream_t stream);
 /* standard-normal / truncated-normal fill with the same Philox stream (testing + generation init). */
 int md_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t step_counter, int64_t elem_offset, float top_p,
                    cudaStream_t stream);

@@ -25,10 +25,10 @@ SIGNATURES = {
     "md_attention_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "md_round_argmin": [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
     "md_logits_argmax": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
-    "md_posterior_step": [c_p, c_p, c_p, c_p, c_p, c_u64, c_u64, c_i64, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p,
-                          c_i, c_i, c_i, c_i, c_f, c_i, c_f, c_p],
-    "md_xstart_from_eps": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
-    "md_q_sample": [c_p, c_p, c_u64, c_u64, c_i64, c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p],
+    "md_posterior_step": [c_p, c_p, c_p, c_p, c_p, c_u64, c_u64, c_i64, c_p, c_i, c_p, c_i64, c_i64, c_p, c_p, c_p,
+                          c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_f, c_p],
+    "md_xstart_from_eps": [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p],
+    "md_q_sample": [c_p, c_p, c_u64, c_u64, c_i64, c_p, c_i, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p],
     "md_fill_normal": [c_p, c_i64, c_u64, c_u64, c_i64, c_f, c_p],
 }
 

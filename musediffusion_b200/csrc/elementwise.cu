@@ -143,11 +143,14 @@ struct StepArgs {
     const float* E;
     const float* noise;
     const int32_t* t;
+    int t_stride;            // 1 = one schedule index per sequence, 0 = one shared by the whole batch
     const int32_t* mask;
     int64_t mask_tok_stride, mask_d_stride;
     const float* x_start;
     float* x_out;
     __nv_bfloat16* out_bf16;
+    float* pred_out;         // optional: processed pred_xstart
+    float* mean_out;         // optional: posterior mean ("greedy_mean")
     int64_t seq_offset;
     int B, L, D;
     float eta;
@@ -166,13 +169,14 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
         const int64_t tok = i / vec_per_tok;
         const int d = (int)(i - tok * vec_per_tok) << 2;
         const int b = (int)(tok / a.L);
-        const int t = a.t[b];
+        const int t = a.t[b * a.t_stride];
         const int64_t off = tok * a.D + d;
         const float4 x = ld_stream_f4(a.x_t + off);
         float4 pr;
         if (a.idx != nullptr) pr = *reinterpret_cast<const float4*>(a.E + (int64_t)a.idx[tok] * a.D + d);
         else pr = ld_stream_f4(a.pred_in + off);
         pr.x = clampf(pr.x, a.clip); pr.y = clampf(pr.y, a.clip); pr.z = clampf(pr.z, a.clip); pr.w = clampf(pr.w, a.clip);
+        if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off, pr);
         float4 n;
         if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
         else n = a.rng.draw4((uint64_t)(((a.seq_offset * a.L) * a.D + off) >> 2));
@@ -183,10 +187,16 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
             // same fp32 op sequence as the reference's torch expression)
             const float c1 = a.sched.get(TAB_C1, t), c2 = a.sched.get(TAB_C2, t);
             const float sd = __fmul_rn(nz, expf(__fmul_rn(0.5f, a.sched.get(TAB_LOGVAR, t))));
-            o.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.x), __fmul_rn(c2, x.x)), __fmul_rn(sd, n.x));
-            o.y = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.y), __fmul_rn(c2, x.y)), __fmul_rn(sd, n.y));
-            o.z = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.z), __fmul_rn(c2, x.z)), __fmul_rn(sd, n.z));
-            o.w = __fadd_rn(__fadd_rn(__fmul_rn(c1, pr.w), __fmul_rn(c2, x.w)), __fmul_rn(sd, n.w));
+            float4 mu;
+            mu.x = __fadd_rn(__fmul_rn(c1, pr.x), __fmul_rn(c2, x.x));
+            mu.y = __fadd_rn(__fmul_rn(c1, pr.y), __fmul_rn(c2, x.y));
+            mu.z = __fadd_rn(__fmul_rn(c1, pr.z), __fmul_rn(c2, x.z));
+            mu.w = __fadd_rn(__fmul_rn(c1, pr.w), __fmul_rn(c2, x.w));
+            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off, mu);
+            o.x = __fadd_rn(mu.x, __fmul_rn(sd, n.x));
+            o.y = __fadd_rn(mu.y, __fmul_rn(sd, n.y));
+            o.z = __fadd_rn(mu.z, __fmul_rn(sd, n.z));
+            o.w = __fadd_rn(mu.w, __fmul_rn(sd, n.w));
         } else {
             const float sr = a.sched.get(TAB_SR, t), srm1 = a.sched.get(TAB_SRM1, t);
             const float ab = a.sched.get(TAB_AB, t), abp = a.sched.get(TAB_ABP, t);
@@ -195,13 +205,18 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
             const float ca = __fsqrt_rn(abp);
             const float cb = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma)));
             const float sn = __fmul_rn(nz, sigma);
-#define MD_DDIM1(X, P, N) \
-    __fadd_rn(__fadd_rn(__fmul_rn(P, ca), __fmul_rn(cb, __fdiv_rn(__fsub_rn(__fmul_rn(sr, X), P), srm1))), __fmul_rn(sn, N))
-            o.x = MD_DDIM1(x.x, pr.x, n.x);
-            o.y = MD_DDIM1(x.y, pr.y, n.y);
-            o.z = MD_DDIM1(x.z, pr.z, n.z);
-            o.w = MD_DDIM1(x.w, pr.w, n.w);
-#undef MD_DDIM1
+#define MD_DDIM_MEAN(X, P) __fadd_rn(__fmul_rn(P, ca), __fmul_rn(cb, __fdiv_rn(__fsub_rn(__fmul_rn(sr, X), P), srm1)))
+            float4 mu;
+            mu.x = MD_DDIM_MEAN(x.x, pr.x);
+            mu.y = MD_DDIM_MEAN(x.y, pr.y);
+            mu.z = MD_DDIM_MEAN(x.z, pr.z);
+            mu.w = MD_DDIM_MEAN(x.w, pr.w);
+#undef MD_DDIM_MEAN
+            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off, mu);
+            o.x = __fadd_rn(mu.x, __fmul_rn(sn, n.x));
+            o.y = __fadd_rn(mu.y, __fmul_rn(sn, n.y));
+            o.z = __fadd_rn(mu.z, __fmul_rn(sn, n.z));
+            o.w = __fadd_rn(mu.w, __fmul_rn(sn, n.w));
         }
         if (a.mask != nullptr) {
             const int32_t* mp = a.mask + tok * a.mask_tok_stride + (int64_t)d * a.mask_d_stride;
@@ -219,12 +234,12 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-xstart_from_eps_kernel(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D, SchedRef s) {
+xstart_from_eps_kernel(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L, int D, SchedRef s) {
     const int vec_per_tok = D >> 2;
     const int64_t total = (int64_t)B * L * vec_per_tok;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t tok = i / vec_per_tok;
-        const int tt = t[tok / L];
+        const int tt = t[(tok / L) * t_stride];
         const float sr = s.get(TAB_SR, tt), srm1 = s.get(TAB_SRM1, tt);
         const float4 x = ld_stream_f4(x_t + i * 4), e = ld_stream_f4(eps + i * 4);
         float4 o;
@@ -240,6 +255,7 @@ struct QSampleArgs {
     const float* x0;
     const float* noise;
     const int32_t* t;
+    int t_stride;
     const int32_t* mask;
     int64_t mask_tok_stride, mask_d_stride;
     float* out;
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const QSampleArgs a) {
         const int64_t tok = i / vec_per_tok;
         const int d = (int)(i - tok * vec_per_tok) << 2;
         const int64_t off = tok * a.D + d;
-        const int t = a.t ? a.t[tok / a.L] : -1;
+        const int t = a.t ? a.t[(tok / a.L) * a.t_stride] : -1;
         const float4 x = ld_stream_f4(a.x0 + off);
         float4 n;
         if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
@@ -498,9 +514,10 @@ extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const vo
 
 extern "C" __attribute__((visibility("default"))) int md_posterior_step(const float* x_t, const int32_t* idx, const float* pred_in, const float* E,
                                  const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
-                                 const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride,
-                                 const float* x_start, float* x_out, void* out_bf16, int B, int L, int D, int mode,
-                                 float eta, int clip, float top_p, cudaStream_t stream) {
+                                 const int32_t* t, int t_stride, const int32_t* mask, int64_t mask_tok_stride,
+                                 int64_t mask_d_stride, const float* x_start, float* x_out, void* out_bf16,
+                                 float* pred_out, float* mean_out, int B, int L, int D, int mode, float eta, int clip,
+                                 float top_p, cudaStream_t stream) {
     if (g_sched_T == 0) { set_last_error("md_posterior_step: md_set_schedule has not been called"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_posterior_step: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((idx == nullptr) == (pred_in == nullptr)) { set_last_error("md_posterior_step: exactly one of idx / pred_in"); return MD_ERR_ARG; }
@@ -509,7 +526,8 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     if (mode != MD_STEP_DDPM && mode != MD_STEP_DDIM) { set_last_error("md_posterior_step: bad mode %d", mode); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
     StepArgs a;
-    a.x_t = x_t; a.idx = idx; a.pred_in = pred_in; a.E = E; a.noise = noise; a.t = t; a.mask = mask;
+    a.x_t = x_t; a.idx = idx; a.pred_in = pred_in; a.E = E; a.noise = noise; a.t = t; a.t_stride = t_stride ? 1 : 0;
+    a.mask = mask; a.pred_out = pred_out; a.mean_out = mean_out;
     a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride; a.x_start = x_start; a.x_out = x_out;
     a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
     a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref();
@@ -519,23 +537,23 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     return check_cuda(cudaGetLastError(), "posterior_step launch");
 }
 
-extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, float* out, int B, int L, int D,
-                                  cudaStream_t stream) {
+extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L,
+                                  int D, cudaStream_t stream) {
     if (g_sched_T == 0) { set_last_error("md_xstart_from_eps: md_set_schedule has not been called"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_xstart_from_eps: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
-    xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, out, B, L, D, sched_ref());
+    xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, t_stride ? 1 : 0, out, B, L, D, sched_ref());
     return check_cuda(cudaGetLastError(), "xstart_from_eps launch");
 }
 
 extern "C" __attribute__((visibility("default"))) int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
-                           const int32_t* t, const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride,
-                           float* out, void* out_bf16, int B, int L, int D, cudaStream_t stream) {
+                           const int32_t* t, int t_stride, const int32_t* mask, int64_t mask_tok_stride,
+                           int64_t mask_d_stride, float* out, void* out_bf16, int B, int L, int D, cudaStream_t stream) {
     if (t != nullptr && g_sched_T == 0) { set_last_error("md_q_sample: md_set_schedule has not been called"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_q_sample: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
     QSampleArgs a;
-    a.x0 = x0; a.noise = noise; a.t = t; a.mask = mask; a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride;
+    a.x0 = x0; a.noise = noise; a.t = t; a.t_stride = t_stride ? 1 : 0; a.mask = mask; a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride;
     a.out = out; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
     a.rng.init(seed, step_counter, 0.0f); a.sched_dev = g_sched_dev; a.T = g_sched_T;
     q_sample_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(a);

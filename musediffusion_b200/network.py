@@ -1,0 +1,272 @@
+"""TransformerNetModel — host-side mirror of MuseDiffusion/models/network.py:20-158 whose forward runs on the
+hand-written sm_100a kernels (tcgen05 GEMMs + fused attention + vectorised LayerNorm) through the C-ABI library.
+
+The module tree reproduces the reference's parameter names exactly (211 state-dict keys at the base config,
+SURVEY.md section 5), so `load_state_dict` of a reference checkpoint works unchanged.  The encoder the reference
+borrows from HF `transformers` (`BertEncoder`, network.py:10,74,151) is restated here as plain parameter holders —
+12 post-LN layers {query,key,value,attention.output.dense+LayerNorm, intermediate.dense, output.dense+LayerNorm} —
+with bert-base-uncased sizes by default (`AutoConfig.from_pretrained('bert-base-uncased')`, network.py:44).
+
+Inference only: dropout (network.py:76,149) is the identity in eval mode, which is the only mode the sampling path
+uses (run/sample.py:88)."""
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+BERT_BASE = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                 layer_norm_eps=1e-12)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.query = nn.Linear(h, h)
+        self.key = nn.Linear(h, h)
+        self.value = nn.Linear(h, h)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, fan_in, h, eps):
+        super().__init__()
+        self.dense = nn.Linear(fan_in, h)
+        self.LayerNorm = nn.LayerNorm(h, eps=eps)
+
+
+class _Attention(nn.Module):
+    def __init__(self, h, eps):
+        super().__init__()
+        self.self = _SelfAttention(h)
+        self.output = _DenseLN(h, h, eps)
+
+
+class _Intermediate(nn.Module):
+    def __init__(self, h, f):
+        super().__init__()
+        self.dense = nn.Linear(h, f)
+
+
+class _Layer(nn.Module):
+    def __init__(self, h, f, eps):
+        super().__init__()
+        self.attention = _Attention(h, eps)
+        self.intermediate = _Intermediate(h, f)
+        self.output = _DenseLN(f, h, eps)
+
+
+class _Encoder(nn.Module):
+    """Parameter holder with HF BertEncoder's key layout (`layer.{i}.…`)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(cfg.hidden_size, cfg.intermediate_size, cfg.layer_norm_eps)
+                                    for _ in range(cfg.num_hidden_layers)])
+
+
+class WeightPack:
+    """Device-resident bf16 / fp32 weights in the layout the kernels consume (built once per parameter version)."""
+
+    def __init__(self, model):
+        dev = model.word_embedding.weight.device
+        if dev.type != "cuda":
+            raise _lib.MuseDiffLibraryError("TransformerNetModel.forward needs the model on a CUDA device "
+                                            "(there is no CPU path); call model.to('cuda') first")
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        self.device = dev
+        self.H = model.hidden_size
+        self.NH = model.num_heads
+        self.eps = model.layer_norm_eps
+        self.E = f32(model.word_embedding.weight)
+        self.lm_bias = f32(model.lm_head.bias)
+        self.t0_w, self.t0_b = f32(model.time_embed[0].weight), f32(model.time_embed[0].bias)
+        self.t2_w, self.t2_b = f32(model.time_embed[2].weight), f32(model.time_embed[2].bias)
+        self.up1_w, self.up1_b = bf(model.input_up_proj[0].weight), f32(model.input_up_proj[0].bias)
+        self.up2_w, self.up2_b = bf(model.input_up_proj[2].weight), f32(model.input_up_proj[2].bias)
+        self.pos = f32(model.position_embeddings.weight)
+        self.ln_g, self.ln_b = f32(model.LayerNorm.weight), f32(model.LayerNorm.bias)
+        self.dn1_w, self.dn1_b = bf(model.output_down_proj[0].weight), f32(model.output_down_proj[0].bias)
+        self.dn2_w, self.dn2_b = bf(model.output_down_proj[2].weight), f32(model.output_down_proj[2].bias)
+        scale = 1.0 / math.sqrt(self.H // self.NH)     # exact power of two for head dim 64: folding it into W_q is lossless
+        self.layers = []
+        for lyr in model.input_transformers.layer:
+            sa = lyr.attention.self
+            wqkv = torch.cat([sa.query.weight.detach().float() * scale, sa.key.weight.detach().float(),
+                              sa.value.weight.detach().float()], dim=0)
+            bqkv = torch.cat([sa.query.bias.detach().float() * scale, sa.key.bias.detach().float(),
+                              sa.value.bias.detach().float()], dim=0)
+            ao, ff = lyr.attention.output, lyr.output
+            self.layers.append(SimpleNamespace(
+                wqkv=bf(wqkv), bqkv=f32(bqkv),
+                wo=bf(ao.dense.weight), bo=f32(ao.dense.bias), g1=f32(ao.LayerNorm.weight), b1=f32(ao.LayerNorm.bias),
+                w1=bf(lyr.intermediate.dense.weight), bi=f32(lyr.intermediate.dense.bias),
+                w2=bf(ff.dense.weight), b2=f32(ff.dense.bias), g2=f32(ff.LayerNorm.weight), b2n=f32(ff.LayerNorm.bias)))
+        # split-bf16 operands for near-fp32 logits on the tensor cores: x.E^T ~ xh.Eh + xh.El + xl.Eh  (K = 3 D)
+        V, D = self.E.shape
+        Vp = (V + 7) // 8 * 8
+        Ep = torch.zeros((Vp, D), dtype=torch.float32, device=dev)
+        Ep[:V] = self.E
+        Eh = Ep.to(torch.bfloat16)
+        El = (Ep - Eh.float()).to(torch.bfloat16)
+        self.E_split = torch.cat([Eh, El, Eh], dim=1).contiguous()
+        self.lm_bias_pad = torch.zeros((Vp,), dtype=torch.float32, device=dev)
+        self.lm_bias_pad[:V] = self.lm_bias
+
+
+class Workspace:
+    """Activation buffers for one token count M (reused across steps: nothing is allocated inside the loop)."""
+
+    def __init__(self, M, D, H, F, dev):
+        bf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)
+        self.M = M
+        self.xb = bf(M, D)
+        self.a = bf(M, H)
+        self.b = bf(M, H)
+        self.c = bf(M, H)
+        self.qkv = bf(M, 3 * H)
+        self.mid = bf(M, F)
+
+
+class TransformerNetModel(nn.Module):
+    """Same constructor, attributes and methods as the reference class (network.py:20-158).
+
+    Extra keyword `encoder_config` overrides the bert-base sizes (used for the scaled-up benchmark config)."""
+
+    def __init__(self, input_dims, output_dims, hidden_t_dim, vocab_size, seq_len, dropout=0.1, logits_mode=1,
+                 encoder_config=None):
+        super().__init__()
+        cfg = SimpleNamespace(**{**BERT_BASE, **(encoder_config or {})})
+        cfg.max_position_embeddings = seq_len
+        cfg.vocab_size = vocab_size
+        self.config = cfg
+        self.input_dims = input_dims
+        self.hidden_t_dim = hidden_t_dim
+        self.output_dims = output_dims
+        self.logits_mode = logits_mode
+        self.hidden_size = cfg.hidden_size
+        self.num_heads = cfg.num_attention_heads
+        self.layer_norm_eps = cfg.layer_norm_eps
+        if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size // cfg.num_attention_heads != 64:
+            raise NotImplementedError("the fused attention kernel is specialised for head dim 64")
+        if input_dims == cfg.hidden_size or output_dims == cfg.hidden_size:
+            raise NotImplementedError("hidden_dim == encoder hidden size (no up/down projection) is not built yet")
+
+        self.word_embedding = nn.Embedding(vocab_size, input_dims)
+        self.lm_head = nn.Linear(input_dims, vocab_size)
+        with torch.no_grad():
+            self.lm_head.weight = self.word_embedding.weight          # tied, network.py:55-58
+        time_embed_dim = hidden_t_dim * 4
+        self.time_embed = nn.Sequential(nn.Linear(hidden_t_dim, time_embed_dim), nn.SiLU(),
+                                        nn.Linear(time_embed_dim, cfg.hidden_size))
+        self.input_up_proj = nn.Sequential(nn.Linear(input_dims, cfg.hidden_size), nn.Tanh(),
+                                           nn.Linear(cfg.hidden_size, cfg.hidden_size))
+        self.input_transformers = _Encoder(cfg)
+        self.dropout = nn.Dropout(dropout)
+        self.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).expand((1, -1)))
+        self.position_embeddings = nn.Embedding(cfg.max_position_embeddings, cfg.hidden_size)
+        self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.output_down_proj = nn.Sequential(nn.Linear(cfg.hidden_size, cfg.hidden_size), nn.Tanh(),
+                                              nn.Linear(cfg.hidden_size, output_dims))
+        self._pack = None
+        self._pack_key = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def weight_pack(self, force=False):
+        key = self._params_key()
+        if force or self._pack is None or key != self._pack_key:
+            self._pack = WeightPack(self)
+            self._pack_key = key
+            self._ws = {}
+        return self._pack
+
+    def workspace(self, M):
+        ws = self._ws.get(M)
+        if ws is None:
+            pk = self.weight_pack()
+            self._ws = {M: Workspace(M, self.input_dims, pk.H, self.config.intermediate_size, pk.device)}
+            ws = self._ws[M]
+        return ws
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def get_embeds(self, input_ids):
+        """network.py:88-89."""
+        return ops.embed_gather(self.weight_pack().E, input_ids)
+
+    def get_logits(self, hidden_repr):
+        """network.py:91-93 (logits_mode 1): lm_head(x) = x E^T + b as ONE tcgen05 GEMM over split-bf16 operands
+        (xh.Eh + xh.El + xl.Eh with fp32 accumulation: ~2^-16 relative, i.e. fp32-grade logits)."""
+        if self.logits_mode != 1:
+            raise NotImplementedError("logits_mode 2 is not used by the sampling path (run/sample.py:219)")
+        pk = self.weight_pack()
+        V, D = pk.E.shape
+        x = hidden_repr.reshape(-1, D).float()
+        xh = x.to(torch.bfloat16)
+        xl = (x - xh.float()).to(torch.bfloat16)
+        A = torch.cat([xh, xh, xl], dim=1).contiguous()
+        out = ops.linear(A, pk.E_split, pk.lm_bias_pad, _lib.EPI_BIAS, out_dtype=torch.float32)
+        return out[:, :V].reshape(*hidden_repr.shape[:-1], V).to(hidden_repr.dtype)
+
+    def decode_tokens(self, hidden_repr, want_margin=False):
+        """get_logits + argmax(-1) (run/sample.py:219-220) fused into one kernel; logits never reach HBM."""
+        pk = self.weight_pack()
+        r = ops.logits_argmax(hidden_repr, pk.E, pk.lm_bias, want_margin=want_margin)
+        if want_margin:
+            return r[0].view(hidden_repr.shape[:-1]).long(), r[1].view(hidden_repr.shape[:-1])
+        return r.view(hidden_repr.shape[:-1]).long()
+
+    @staticmethod
+    def timestep_embedding(timesteps, dim, max_period=10000):
+        """network.py:108-129 (kept for API parity; the forward path computes it inside md_timestep_mlp)."""
+        half = dim // 2
+        freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device) / half)
+        args = timesteps[:, None].float() * freqs[None]
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+        if dim % 2:
+            emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+        return emb
+
+    def forward(self, x, timesteps, **_):
+        """network.py:131-158.  x: [B, L, D] float, timesteps: [B] (int or float).  Returns [B, L, D] in x.dtype."""
+        return self.denoise(x, timesteps).type(x.dtype)
+
+    # ------------------------------------------------------------------------------------------ engine
+    def denoise(self, x, timesteps, x_bf16=None, uniform_t=False, out=None):
+        """The CUDA forward.  `x_bf16`: optional bf16 copy of x already produced by the posterior-step kernel;
+        `uniform_t`: all rows share timesteps[0] (true inside the sampling loops) -> one time-embedding row."""
+        pk = self.weight_pack()
+        if not x.is_cuda:
+            raise _lib.MuseDiffLibraryError("TransformerNetModel.forward needs CUDA tensors (no CPU path)")
+        B, L, D = x.shape
+        if L > self.config.max_position_embeddings:
+            raise ValueError("sequence length %d exceeds seq_len %d" % (L, self.config.max_position_embeddings))
+        M, H = B * L, pk.H
+        ws = self.workspace(M)
+        E = _lib
+        xb = x_bf16.view(M, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(M, D).float())
+        t = timesteps.reshape(-1).float()
+        temb = ops.timestep_mlp(t[:1] if uniform_t else t, pk.t0_w, pk.t0_b, pk.t2_w, pk.t2_b)
+        ops.linear(xb, pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=ws.a)
+        ops.linear(ws.a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,
+                   temb_stride=0 if uniform_t else H, L=L, out=ws.b)
+        h, h1, pre = ws.a, ws.c, ws.b
+        ops.layernorm(pre, pk.ln_g, pk.ln_b, pk.eps, out=h)
+        for ly in pk.layers:
+            ops.linear(h, ly.wqkv, ly.bqkv, E.EPI_BIAS, out=ws.qkv)
+            ops.attention(ws.qkv, B, L, pk.NH, out=h1)                       # ctx -> h1 buffer
+            ops.linear(h1, ly.wo, ly.bo, E.EPI_BIAS_RESID, resid=h, out=pre)
+            ops.layernorm(pre, ly.g1, ly.b1, pk.eps, out=h1)
+            ops.linear(h1, ly.w1, ly.bi, E.EPI_BIAS_GELU, out=ws.mid)
+            ops.linear(ws.mid, ly.w2, ly.b2, E.EPI_BIAS_RESID, resid=h1, out=pre)
+            ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, out=h)
+        ops.linear(h, pk.dn1_w, pk.dn1_b, E.EPI_BIAS_TANH, out=h1)
+        if out is None:
+            out = torch.empty((M, D), dtype=torch.float32, device=x.device)
+        ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS, out=out.view(M, D))
+        return out.view(B, L, D)

@@ -6,9 +6,41 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call
 
 BF16 = torch.bfloat16
+
+_LAUNCHES = [0]
+_PROFILE = [None]      # list of (name, detail, start_event, end_event) while profile_step() is active
+
+
+def call(name, *args, detail=""):
+    """one C-ABI call == one kernel launch of ours (md_set_schedule only copies tables)."""
+    prof = _PROFILE[0]
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        prof.append((name, detail, e0, e1))
+    else:
+        _lib.call(name, *args)
+    if name != "md_set_schedule":
+        _LAUNCHES[0] += 1
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
+def profile_step(fn):
+    """run fn() with CUDA events around every kernel launch; returns [(kernel, detail, ms)]."""
+    _PROFILE[0] = []
+    try:
+        fn()
+        torch.cuda.synchronize()
+        return [(n, d, e0.elapsed_time(e1)) for n, d, e0, e1 in _PROFILE[0]]
+    finally:
+        _PROFILE[0] = None
 
 
 def _stream():
@@ -36,10 +68,14 @@ TABLE_ORDER = ["posterior_mean_coef1", "posterior_mean_coef2", "model_log_varian
 _current_schedule_key = [None]
 
 
+def current_schedule_key():
+    return _current_schedule_key[0]
+
+
 def set_schedule(tables64, key=None):
     """tables64: dict name -> float64 numpy [T].  Cast to fp32 exactly like _extract_into_tensor
     (MuseDiffusion/models/diffusion.py:914) and uploaded once; `key` lets callers skip redundant uploads."""
-    if key is not None and _current_schedule_key[0] == key:
+    if key is not None and _current_schedule_key[0] is key:
         return
     T = len(tables64[TABLE_ORDER[0]])
     host = np.ascontiguousarray(np.stack([np.asarray(tables64[n], dtype=np.float64).astype(np.float32)
@@ -95,7 +131,7 @@ def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, resid=None, pos=N
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     call("md_linear_bf16", _p(A), _p(W), _p(bias), _p(out), M, N, K, epilogue, int(out.dtype == torch.float32),
-         _p(resid), _p(pos), _p(temb), temb_stride, L, _stream())
+         _p(resid), _p(pos), _p(temb), temb_stride, L, _stream(), detail="%dx%dx%d epi=%d" % (M, N, K, epilogue))
     return out
 
 
@@ -149,11 +185,22 @@ def _mask_args(mask, B, L, D):
     return full, full, D, 1
 
 
+def _t_args(t, B):
+    """t: int tensor with B entries (one schedule index per sequence) or 1 entry (shared by the batch)."""
+    t = _c(t.reshape(-1), torch.int32)
+    if t.numel() == B and B != 1:
+        return t, 1
+    if t.numel() == 1:
+        return t, 0
+    raise ValueError("timestep tensor has %d entries for a batch of %d" % (t.numel(), B))
+
+
 def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0, step_counter=0, seq_offset=0,
-                   mask=None, x_start=None, eta=0.0, clip=True, top_p=0.0, out=None, out_bf16=None):
+                   mask=None, x_start=None, eta=0.0, clip=True, top_p=0.0, out=None, out_bf16=None, pred_out=None,
+                   mean_out=None):
     x_t = _c(x_t, torch.float32)
     B, L, D = x_t.shape
-    t = _c(t, torch.int32)
+    t, t_stride = _t_args(t, B)
     keep, mask_t, ts, ds = _mask_args(mask, B, L, D)
     if out is None:
         out = torch.empty_like(x_t)
@@ -166,8 +213,8 @@ def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0
     if idx is not None:
         idx = _c(idx, torch.int32)
     call("md_posterior_step", _p(x_t), _p(idx), _p(pred), _p(E), _p(noise), int(seed), int(step_counter),
-         int(seq_offset), _p(t), _p(mask_t), ts, ds, _p(x_start), _p(out), _p(out_bf16), B, L, D, mode, float(eta),
-         int(bool(clip)), float(top_p or 0.0), _stream())
+         int(seq_offset), _p(t), t_stride, _p(mask_t), ts, ds, _p(x_start), _p(out), _p(out_bf16), _p(pred_out),
+         _p(mean_out), B, L, D, mode, float(eta), int(bool(clip)), float(top_p or 0.0), _stream())
     return out
 
 
@@ -176,7 +223,8 @@ def xstart_from_eps(x_t, eps, t):
     eps = _c(eps, torch.float32)
     B, L, D = x_t.shape
     out = torch.empty_like(x_t)
-    call("md_xstart_from_eps", _p(x_t), _p(eps), _p(_c(t, torch.int32)), _p(out), B, L, D, _stream())
+    t, t_stride = _t_args(t, B)
+    call("md_xstart_from_eps", _p(x_t), _p(eps), _p(t), t_stride, _p(out), B, L, D, _stream())
     return out
 
 
@@ -188,8 +236,8 @@ def q_sample(x0, t=None, noise=None, seed=0, step_counter=0, seq_offset=0, mask=
     out = torch.empty_like(x0)
     if noise is not None:
         noise = _c(noise, torch.float32)
-    tt = _c(t, torch.int32) if t is not None else None
-    call("md_q_sample", _p(x0), _p(noise), int(seed), int(step_counter), int(seq_offset), _p(tt), _p(mask_t), ts, ds,
+    tt, t_stride = _t_args(t, B) if t is not None else (None, 0)
+    call("md_q_sample", _p(x0), _p(noise), int(seed), int(step_counter), int(seq_offset), _p(tt), t_stride, _p(mask_t), ts, ds,
          _p(out), _p(out_bf16), B, L, D, _stream())
     return out
 

@@ -1,0 +1,132 @@
+"""The hot slice of MuseDiffusion/run/sample.py (:84-114 set-up, :177-220 per-batch sampling) as a library call plus a
+small command line with the reference's sub-commands and flag names (`generation` / `modification`;
+MuseDiffusion/config/sample.py:93-112,137-209).  MIDI decoding, metrics and the dataset pipeline stay with the
+reference (out of scope): this entry point reads token batches (.npz) or synthesises
+ComMU-shaped ones and writes decoded token ids."""
+import argparse
+import json
+import os
+import time
+from functools import partial
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import ops
+from .initialization import create_model_and_diffusion, seed_all
+from .rounding import denoised_fn_round
+
+
+def build_model_emb(model, device):
+    """run/sample.py:92-101: frozen copy of the word embedding used by the rounding callback."""
+    w = model.word_embedding.weight
+    emb = torch.nn.Embedding(num_embeddings=w.shape[0], embedding_dim=w.shape[1], padding_idx=0,
+                             _weight=w.detach().clone())
+    return emb.eval().requires_grad_(False).to(device)
+
+
+@torch.no_grad()
+def sample_batch(model, diffusion, model_emb, cond, mode, step, diffusion_steps, strength=0.75, top_p=1, clamp_step=0,
+                 clip_denoised=True, device=None, fused_decode=True):
+    """run/sample.py:177-220 for one batch: cond = {'input_ids', 'input_mask'} (host or device int tensors) ->
+    int64 token ids [B, L] on the device.  `fused_decode=False` keeps the reference's get_logits + argmax pair."""
+    device = device or next(model.parameters()).device
+    input_ids = torch.as_tensor(cond["input_ids"]).to(device, non_blocking=True)
+    mask_ori = torch.as_tensor(cond["input_mask"]).to(device, non_blocking=True)
+    x_start = model.get_embeds(input_ids)                                               # :185
+    input_ids_mask = torch.broadcast_to(mask_ori.unsqueeze(dim=-1), x_start.shape)      # :186
+    if mode == "generation":                                                            # :190-193
+        noising_t = None
+        if diffusion.noise_source is not None:
+            noise = diffusion._external_noise(x_start.shape, "randn", device)
+        else:
+            noise = None
+        x_noised = ops.q_sample(x_start, None, noise=noise, seed=diffusion._seed(),
+                                step_counter=diffusion._next_counter(), seq_offset=diffusion.seq_offset, mask=mask_ori)
+    else:                                                                               # :195-197
+        noising_t = int(step * strength)
+        timestep = torch.full((x_start.shape[0], 1), noising_t - 1, device=device)
+        x_noised = diffusion.q_sample(x_start.unsqueeze(-1), timestep, mask=input_ids_mask).squeeze(-1)
+    if step == diffusion_steps:                                                         # :109-114
+        gap, sample_fn = 1, diffusion.p_sample_loop
+    else:
+        gap, sample_fn = diffusion_steps // step, diffusion.ddim_sample_loop
+    samples = sample_fn(model=model, shape=tuple(x_start.shape), noise=x_noised, clip_denoised=clip_denoised,
+                        denoised_fn=partial(denoised_fn_round, model_emb, dist=None), model_kwargs=cond, top_p=top_p,
+                        clamp_step=clamp_step, clamp_first=True, mask=input_ids_mask, x_start=x_start, gap=gap,
+                        t_enc=noising_t, only_last=True)                                # :200-215
+    sample = samples[-1]
+    if fused_decode:
+        return model.decode_tokens(sample)
+    return torch.argmax(model.get_logits(sample), dim=-1)                               # :219-220
+
+
+def load_training_args(model_path):
+    """config/sample.py:114-134: `training_args.json` sits next to the checkpoint."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(model_path)), "training_args.json")) as f:
+        return SimpleNamespace(**json.load(f))
+
+
+def create_parser():
+    p = argparse.ArgumentParser(prog="python -m musediffusion_b200")
+    sub = p.add_subparsers(dest="mode", required=True)
+    for name in ("generation", "modification"):
+        sp = sub.add_parser(name)
+        sp.add_argument("--model_path", required=True)
+        sp.add_argument("--step", type=int, default=100)
+        sp.add_argument("--out_dir", default="./out")
+        sp.add_argument("--batch_size", type=int, default=50)
+        sp.add_argument("--top_p", type=int, default=1)
+        sp.add_argument("--clamp_step", type=int, default=0)
+        sp.add_argument("--sample_seed", type=int, default=105)
+        sp.add_argument("--clip_denoised", type=lambda s: s.lower() in ("1", "true", "yes"), default=True)
+        sp.add_argument("--input_npz", default=None, help="npz with input_ids/input_mask [N, L] (else synthetic)")
+        if name == "modification":
+            sp.add_argument("--strength", type=float, default=0.75)
+            sp.add_argument("--num_batches", type=int, default=1)
+        else:
+            sp.add_argument("--num_samples", type=int, default=1000)
+    return p
+
+
+def main(argv=None):
+    args = create_parser().parse_args(argv)
+    from . import dist
+    rank, world, dev = dist.setup()
+    targs = load_training_args(args.model_path)
+    model, diffusion = create_model_and_diffusion(targs)
+    model.load_state_dict(torch.load(args.model_path, map_location="cpu"))
+    model.eval().requires_grad_(False).to(dev)
+    model_emb = build_model_emb(model, dev)
+    seed_all(args.sample_seed, deterministic=True)
+    if args.input_npz:
+        data = np.load(args.input_npz)
+        ids_all, mask_all = data["input_ids"], data["input_mask"]
+    else:
+        from .synthetic import make_synthetic_batch
+        n = args.num_samples if args.mode == "generation" else args.batch_size * args.num_batches
+        b = make_synthetic_batch(args.mode, n, targs.seq_len, seed=args.sample_seed)
+        ids_all, mask_all = b["input_ids"], b["input_mask"]
+    out_dir = os.path.join(args.out_dir, os.path.basename(os.path.dirname(os.path.abspath(args.model_path))),
+                           os.path.basename(args.model_path) + "." + args.mode + ".samples")
+    os.makedirs(out_dir, exist_ok=True)
+    tic = time.time()
+    tokens = []
+    n_batches = (len(ids_all) + args.batch_size - 1) // args.batch_size
+    for bi in range(n_batches):
+        if bi % world != rank:                                    # run/sample.py:169-172
+            continue
+        sl = slice(bi * args.batch_size, (bi + 1) * args.batch_size)
+        diffusion.seq_offset = sl.start
+        cond = {"input_ids": torch.from_numpy(ids_all[sl]), "input_mask": torch.from_numpy(mask_all[sl])}
+        tok = sample_batch(model, diffusion, model_emb, cond, args.mode, args.step, targs.diffusion_steps,
+                           strength=getattr(args, "strength", 0.75), top_p=args.top_p, clamp_step=args.clamp_step,
+                           clip_denoised=args.clip_denoised, device=dev)
+        tokens.append((bi, tok.cpu().numpy()))
+    gathered = dist.gather_objects(tokens)
+    if rank == 0:
+        flat = [t for _, t in sorted(sum(gathered, []), key=lambda p: p[0])]
+        np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
+        print("### Total takes %.2fs; %d sequences -> %s" % (time.time() - tic, sum(len(t) for t in flat), out_dir))
+    dist.barrier()
