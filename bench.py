@@ -172,7 +172,7 @@ def run_ours(args):
                                   mask=mask).squeeze(-1)
     n_total = DIFFUSION_STEPS if args.full_chain else args.warmup + args.steps
     gen = diffusion._loop(_lib.STEP_DDPM, model, tuple(x_start.shape), x_noised, True, fn, None, dev, False, 1, 0, True,
-                          mask, x_start, 0.0, list(range(DIFFUSION_STEPS))[::-1][:n_total], want_aux=False)
+                          mask, x_start, 0.0, list(range(DIFFUSION_STEPS))[::-1][:n_total + 1], want_aux=False)
     sampler = ClockSampler(dev.index or 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     last = None

@@ -58,7 +58,8 @@ int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out,
 /* timestep_embedding + time_embed MLP (models/network.py:108-129, 60-65, 139):
  * out[b, :] = W2 silu(W0 [cos(t f), sin(t f)] + b0) + b2, fp32 throughout.  t is the float fed to the model. */
 int md_timestep_mlp(const float* t, const float* W0, const float* b0, const float* W2, const float* b2, float* out,
-                    int B, int t_dim, int mid_dim, int out_dim, cudaStream_t stream);
+                    float* hidden_ws /* [B, mid_dim] scratch */, int B, int t_dim, int mid_dim, int out_dim,
+                    cudaStream_t stream);
 /* LayerNorm over the last dim of a bf16 [M, H] tensor, fp32 statistics (network.py:149 and the HF Bert
  * LayerNorms, eps = 1e-12).  H must be a multiple of 256 and <= 2048. */
 int md_layernorm_bf16(const void* in_bf16, const float* gamma, const float* beta, float eps, void* out_bf16,

@@ -19,7 +19,7 @@ SIGNATURES = {
     "md_set_schedule": [c_p, c_i, c_p],
     "md_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
     "md_embed_gather": [c_p, c_p, c_i, c_p, c_i64, c_i, c_i, c_p],
-    "md_timestep_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "md_timestep_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "md_layernorm_bf16": [c_p, c_p, c_p, c_f, c_p, c_i64, c_i, c_p],
     "md_linear_bf16": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p],
     "md_attention_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],

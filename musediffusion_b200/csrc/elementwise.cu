@@ -387,16 +387,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 }
 
 // ----------------------------------------------------------------------------------------------
-// timestep embedding + time_embed MLP: one block per sequence, fp32, warp-per-output-row dot products
+// timestep embedding + time_embed MLP, fp32, warp-per-output-row dot products.  Two launches (hidden layer, output
+// layer), each spread over B x row-chunks CTAs: inside the sampling loops B is 1 (all sequences share t), so a
+// single-CTA formulation would stream the 1.5 MB second weight matrix through one SM.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) timestep_mlp_kernel(const float* __restrict__ t, const float* __restrict__ W0,
-                                                           const float* __restrict__ b0, const float* __restrict__ W2,
-                                                           const float* __restrict__ b2, float* __restrict__ out, int t_dim,
-                                                           int mid_dim, int out_dim) {
-    extern __shared__ float sm[];
-    float* emb = sm;            // [t_dim]
-    float* hid = sm + t_dim;    // [mid_dim]
-    const int b = blockIdx.x;
+constexpr int kTmlpRowsPerCta = 32;
+__global__ void __launch_bounds__(256) timestep_hidden_kernel(const float* __restrict__ t, const float* __restrict__ W0,
+                                                              const float* __restrict__ b0, float* __restrict__ hid,
+                                                              int t_dim, int mid_dim) {
+    extern __shared__ float emb[];   // [t_dim]
+    const int b = blockIdx.y;
     const int half = t_dim / 2;
     const float tv = t[b];
     for (int k = threadIdx.x; k < t_dim; k += blockDim.x) {
@@ -412,20 +412,30 @@ __global__ void __launch_bounds__(256) timestep_mlp_kernel(const float* __restri
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < mid_dim; r += nw) {
+    const int r0 = blockIdx.x * kTmlpRowsPerCta;
+    for (int r = r0 + warp; r < min(r0 + kTmlpRowsPerCta, mid_dim); r += nw) {
         float acc = 0.f;
         for (int k = lane; k < t_dim; k += 32) acc = fmaf(W0[(size_t)r * t_dim + k], emb[k], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
             const float z = acc + b0[r];
-            hid[r] = z / (1.0f + expf(-z));   // SiLU
+            hid[(size_t)b * mid_dim + r] = z / (1.0f + expf(-z));   // SiLU
         }
     }
+}
+__global__ void __launch_bounds__(256) timestep_out_kernel(const float* __restrict__ hid, const float* __restrict__ W2,
+                                                           const float* __restrict__ b2, float* __restrict__ out,
+                                                           int mid_dim, int out_dim) {
+    extern __shared__ float hs[];    // [mid_dim]
+    const int b = blockIdx.y;
+    for (int k = threadIdx.x; k < mid_dim; k += blockDim.x) hs[k] = hid[(size_t)b * mid_dim + k];
     __syncthreads();
-    for (int r = warp; r < out_dim; r += nw) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int r0 = blockIdx.x * kTmlpRowsPerCta;
+    for (int r = r0 + warp; r < min(r0 + kTmlpRowsPerCta, out_dim); r += nw) {
         float acc = 0.f;
-        for (int k = lane; k < mid_dim; k += 32) acc = fmaf(W2[(size_t)r * mid_dim + k], hid[k], acc);
+        for (int k = lane; k < mid_dim; k += 32) acc = fmaf(W2[(size_t)r * mid_dim + k], hs[k], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) out[(size_t)b * out_dim + r] = acc + b2[r];
@@ -485,10 +495,12 @@ extern "C" __attribute__((visibility("default"))) int md_embed_gather(const floa
 }
 
 extern "C" __attribute__((visibility("default"))) int md_timestep_mlp(const float* t, const float* W0, const float* b0, const float* W2, const float* b2,
-                               float* out, int B, int t_dim, int mid_dim, int out_dim, cudaStream_t stream) {
+                               float* out, float* hidden_ws, int B, int t_dim, int mid_dim, int out_dim, cudaStream_t stream) {
     if (B <= 0) return MD_OK;
-    const size_t smem = sizeof(float) * (t_dim + mid_dim);
-    timestep_mlp_kernel<<<B, 256, smem, stream>>>(t, W0, b0, W2, b2, out, t_dim, mid_dim, out_dim);
+    if (hidden_ws == nullptr) { set_last_error("md_timestep_mlp: hidden workspace [B, mid_dim] missing"); return MD_ERR_ARG; }
+    dim3 g1((mid_dim + kTmlpRowsPerCta - 1) / kTmlpRowsPerCta, B), g2((out_dim + kTmlpRowsPerCta - 1) / kTmlpRowsPerCta, B);
+    timestep_hidden_kernel<<<g1, 256, sizeof(float) * t_dim, stream>>>(t, W0, b0, hidden_ws, t_dim, mid_dim);
+    timestep_out_kernel<<<g2, 256, sizeof(float) * mid_dim, stream>>>(hidden_ws, W2, b2, out, mid_dim, out_dim);
     return check_cuda(cudaGetLastError(), "timestep_mlp launch");
 }
 

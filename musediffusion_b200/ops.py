@@ -106,8 +106,9 @@ def embed_gather(E, ids):
 def timestep_mlp(t, W0, b0, W2, b2):
     t = _c(t, torch.float32)
     out = torch.empty((t.numel(), W2.shape[0]), dtype=torch.float32, device=t.device)
-    call("md_timestep_mlp", _p(t), _p(W0), _p(b0), _p(W2), _p(b2), _p(out), t.numel(), W0.shape[1], W0.shape[0],
-         W2.shape[0], _stream())
+    hid = torch.empty((t.numel(), W0.shape[0]), dtype=torch.float32, device=t.device)
+    call("md_timestep_mlp", _p(t), _p(W0), _p(b0), _p(W2), _p(b2), _p(out), _p(hid), t.numel(), W0.shape[1],
+         W0.shape[0], W2.shape[0], _stream())
     return out
 
 
