@@ -29,7 +29,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define MD_EPI_BIAS 0          /* y = xW^T + b                                                           */
 #define MD_EPI_BIAS_GELU 1     /* erf-GELU(y)            HF BertIntermediate (called from network.py:151) */
 #define MD_EPI_BIAS_TANH 2     /* tanh(y)                input_up_proj / output_down_proj, network.py:69-70,83-84 */
-#define MD_EPI_BIAS_RESID 3    /* y + residual           HF BertSelfOutput / BertOutput pre-LayerNorm sum */
+/* (3 is reserved: the residual add of HF BertSelfOutput / BertOutput is fused into md_layernorm_bf16 instead) */
 #define MD_EPI_BIAS_POS_TIME 4 /* y + pos[l] + temb[b]   network.py:146-148 pre-LayerNorm sum            */
 
 /* modes of md_posterior_step */
@@ -60,18 +60,18 @@ int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out,
 int md_timestep_mlp(const float* t, const float* W0, const float* b0, const float* W2, const float* b2, float* out,
                     float* hidden_ws /* [B, mid_dim] scratch */, int B, int t_dim, int mid_dim, int out_dim,
                     cudaStream_t stream);
-/* LayerNorm over the last dim of a bf16 [M, H] tensor, fp32 statistics (network.py:149 and the HF Bert
- * LayerNorms, eps = 1e-12).  H must be a multiple of 256 and <= 2048. */
-int md_layernorm_bf16(const void* in_bf16, const float* gamma, const float* beta, float eps, void* out_bf16,
-                      int64_t M, int H, cudaStream_t stream);
+/* out = LayerNorm(in + resid) over the last dim of bf16 [M, H] tensors, fp32 statistics (network.py:149 and the HF
+ * BertSelfOutput / BertOutput `LayerNorm(dense(x) + input)`, eps = 1e-12).  resid may be NULL.  H must be a multiple
+ * of 256 and <= 2048. */
+int md_layernorm_bf16(const void* in_bf16, const void* resid_bf16, const float* gamma, const float* beta, float eps,
+                      void* out_bf16, int64_t M, int H, cudaStream_t stream);
 
 /* ---- dense contractions (tcgen05 / TMEM / TMA) ---- */
 /* nn.Linear with fused epilogue: out[M,N] = epi(A[M,K] W[N,K]^T + bias).  A, W bf16; bias/pos/temb fp32;
- * out bf16 (out_is_f32 = 0) or fp32.  resid: bf16 [M,N] (MD_EPI_BIAS_RESID).  pos: [L,N], temb: [M/L or 1, N] with
- * row stride temb_stride (0 = one shared row) (MD_EPI_BIAS_POS_TIME).  K, N multiples of 8. */
+ * out bf16 (out_is_f32 = 0) or fp32.  pos: [L,N], temb: [M/L or 1, N] with row stride temb_stride (0 = one shared
+ * row) (MD_EPI_BIAS_POS_TIME).  K, N multiples of 8; A, W, out 16-byte aligned. */
 int md_linear_bf16(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epilogue,
-                   int out_is_f32, const void* resid, const float* pos, const float* temb, int temb_stride, int L,
-                   cudaStream_t stream);
+                   int out_is_f32, const float* pos, const float* temb, int temb_stride, int L, cudaStream_t stream);
 /* HF BertSelfAttention without mask (called from network.py:151): qkv bf16 [B*L, 3*NH*DH] laid out
  * [q heads | k heads | v heads] per token, q already scaled by 1/sqrt(DH); out bf16 [B*L, NH*DH] = softmax(qk^T) v.
  * DH must be 64. */

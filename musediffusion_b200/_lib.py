@@ -20,8 +20,8 @@ SIGNATURES = {
     "md_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
     "md_embed_gather": [c_p, c_p, c_i, c_p, c_i64, c_i, c_i, c_p],
     "md_timestep_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
-    "md_layernorm_bf16": [c_p, c_p, c_p, c_f, c_p, c_i64, c_i, c_p],
-    "md_linear_bf16": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p],
+    "md_layernorm_bf16": [c_p, c_p, c_p, c_p, c_f, c_p, c_i64, c_i, c_p],
+    "md_linear_bf16": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
     "md_attention_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "md_round_argmin": [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
     "md_logits_argmax": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
@@ -32,7 +32,7 @@ SIGNATURES = {
     "md_fill_normal": [c_p, c_i64, c_u64, c_u64, c_i64, c_f, c_p],
 }
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_RESID, EPI_BIAS_POS_TIME = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_POS_TIME = 0, 1, 2, 4
 STEP_DDPM, STEP_DDIM = 0, 1
 MAX_CONST_T = 2048
 

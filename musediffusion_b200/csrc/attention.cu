@@ -13,8 +13,11 @@
 // One persistent CTA per SM works on TWO 128-row Q tiles of the same (b, h) so the tensor pipe computes S for one
 // tile while the other tile's softmax runs, and both tiles share every K/V stage brought in by TMA.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = softmax/correction/epilogue for Q tile 0, warps 6..9 = same for Q tile 1.
+// Roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0: TMA producer, warp 1: TMEM owner + single-thread MMA
+// issuer, warps 2-3: idle}, warpgroup 1 = softmax/correction/epilogue for Q tile 0, warpgroup 2 = same for Q tile 1.
+// setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (a full S row lives in registers), and a
+// pair of named barriers makes the two softmax warpgroups take turns on the exp2 (MUFU) phase: at head dim 64 the
+// MUFU pipe, not the tensor pipe, is the binding unit, so its phases must never idle or overlap.
 #include "common.cuh"
 #include "musediff_b200.h"
 
@@ -27,7 +30,8 @@ constexpr int ATT_BQ = 128;        // rows per Q tile
 constexpr int ATT_BKV = 128;       // keys per K/V stage
 constexpr int ATT_DH = 64;
 constexpr int ATT_STAGES = 3;
-constexpr int kAttThreads = 320;
+constexpr int kAttThreads = 384;
+constexpr int kRegsProducer = 80, kRegsSoftmax = 216;   // 128*80 + 256*216 = 65536
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;   // TMEM columns
@@ -51,6 +55,15 @@ MD_DEVINL Work decode_work(int w, const AttArgs& a) {
     r.h = bh % a.NH;
     r.b = bh / a.NH;
     return r;
+}
+
+MD_DEVINL void turn_wait(int x) {
+    if (x == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+    else asm volatile("bar.sync 3, 256;" ::: "memory");
+}
+MD_DEVINL void turn_pass(int x) {
+    if (x == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+    else asm volatile("bar.arrive 2, 256;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kAttThreads, 1)
@@ -101,6 +114,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     if (warp == 0) {
         // =========================================================== TMA producer
         if (lane == 0) {
@@ -138,13 +153,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             auto issue_qk = [&](int x, int st) {
                 const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
                 const uint64_t kd = make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(tS[x], qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
                 tc_commit(&s_full[x]);
             };
             auto issue_pv = [&](int x, int st, bool accumulate) {
                 const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < ATT_BKV / 16; ++k)   // 16 keys = 8 packed TMEM columns of P, 2048 B of V rows
                     umma_ts(tO[x], tS[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
             };
@@ -156,7 +171,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     const int st = kcnt % ATT_STAGES;
                     mbar_wait(&k_full[st], (kcnt / ATT_STAGES) & 1);
                     tc_fence_after();
-                    for (int x = 0; x < n_active; ++x) issue_qk(x, st);
+#pragma unroll
+                    for (int x = 0; x < 2; ++x)
+                        if (x < n_active) issue_qk(x, st);
                     tc_commit(&k_empty[st]);
                 }
                 for (int j = 0; j < a.n_kv; ++j) {
@@ -167,7 +184,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     const bool has_next = (j + 1 < a.n_kv);
                     mbar_wait(&v_full[st], ph);
                     if (has_next) mbar_wait(&k_full[st_n], ph_n);
-                    for (int x = 0; x < n_active; ++x) {
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        if (x >= n_active) continue;
                         if (j == 0) mbar_wait(&o_empty[x], (ocnt[x] & 1) ^ 1);   // previous item's O drained
                         mbar_wait(&p_full[x], pcnt[x] & 1);
                         ++pcnt[x];
@@ -183,9 +202,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 kcnt += a.n_kv;
             }
         }
+    }
     } else {
         // =========================================================== softmax / correction / epilogue
-        const int x = (warp - 2) >> 2;          // which Q tile this warpgroup owns
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+        const int x = (warp - 4) >> 2;          // which Q tile this warpgroup owns
+        // turn-taking on the exp2 phase: warpgroup x syncs on barrier (2 + x) and hands over by arriving on (3 - x)
+        if (x == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 goes first
         const int quad = warp & 3;              // TMEM lane quadrant
         const int r = quad * 32 + lane;         // row inside the Q tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -195,38 +218,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
             const Work wk = decode_work(w, a);
             const int qt = wk.pair * 2 + x;
-            if (qt >= a.n_qtiles) continue;
+            if (qt >= a.n_qtiles) {
+                // phantom tile of the last pair: keep the turn-taking handshake in step with the other warpgroup
+                for (int j = 0; j < a.n_kv; ++j) {
+                    turn_wait(x);
+                    turn_pass(x);
+                }
+                continue;
+            }
             float m_used = 0.f, l_sum = 0.f;
             for (int j = 0; j < a.n_kv; ++j, ++scnt) {
                 mbar_wait(&s_full[x], scnt & 1);
                 tc_fence_after();
-                uint32_t s[128];
-                {
-                    uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                    uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-                    uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-                    tmem_ld32(tS + 0, s0);
-                    tmem_ld32(tS + 32, s1);
-                    tmem_ld32(tS + 64, s2);
-                    tmem_ld32(tS + 96, s3);
-                }
+                uint32_t s[4][32];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tmem_ld32(tS + 32 * g, s[g]);
                 tc_wait_ld();
                 const int valid = a.L - j * ATT_BKV;   // keys in this block that exist
                 if (valid < ATT_BKV) {
 #pragma unroll
-                    for (int c = 0; c < 128; ++c)
-                        if (c >= valid) s[c] = 0xff800000u;   // -inf
-                }
-                float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-                      mx3 = __uint_as_float(s[3]);
+                    for (int g = 0; g < 4; ++g)
 #pragma unroll
-                for (int c = 4; c < 128; c += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[c]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                        for (int c = 0; c < 32; ++c)
+                            if (g * 32 + c >= valid) s[g][c] = 0xff800000u;   // -inf
                 }
+                float mx0 = __uint_as_float(s[0][0]), mx1 = __uint_as_float(s[0][1]), mx2 = __uint_as_float(s[0][2]),
+                      mx3 = __uint_as_float(s[0][3]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int c = (g == 0 ? 4 : 0); c < 32; c += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[g][c]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[g][c + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[g][c + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[g][c + 3]));
+                    }
                 const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;
                 if (j == 0) {
                     m_used = mb;
@@ -251,18 +277,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     }
                 }
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                turn_wait(x);                                                   // my turn on the MUFU pipe
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(s[g * 32 + 2 * c]), kLog2e, -m_used));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(s[g * 32 + 2 * c + 1]), kLog2e, -m_used));
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(s[g][2 * c]), kLog2e, -m_used));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(s[g][2 * c + 1]), kLog2e, -m_used));
                         if (c & 1) { acc2 += p0; acc3 += p1; } else { acc0 += p0; acc1 += p1; }
                         pk[c] = pack_bf16x2(p0, p1);
                     }
                     tmem_st16(tS + g * 16, pk);    // P overwrites the first 64 columns of S (row already in registers)
                 }
+                turn_pass(x);                                                   // hand the MUFU pipe to the other tile
                 l_sum += (acc0 + acc1) + (acc2 + acc3);
                 tc_wait_st();
                 tc_fence_before();
@@ -304,6 +332,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         }
     }
     __syncwarp();
+    if (warp >= 4 && warp < 8) asm volatile("bar.sync 2, 256;" ::: "memory");   // absorb tile 1's final hand-over
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);

@@ -337,9 +337,10 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const float* E, const
 // LayerNorm (bf16 in/out, fp32 statistics), one warp per row
 // ----------------------------------------------------------------------------------------------
 template <int VEC>  // VEC 16-byte vectors (8 bf16) per lane: H = 256 * VEC
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float eps,
-                                                        __nv_bfloat16* __restrict__ out, int64_t M) {
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in,
+                                                        const __nv_bfloat16* __restrict__ resid,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ out, int64_t M) {
     constexpr int H = 256 * VEC;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -347,13 +348,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     for (int64_t row = warp_global; row < M; row += nwarps) {
         const __nv_bfloat16* p = in + row * H;
         float v[VEC * 8];
+        uint4 u[VEC], ur[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) u[j] = *reinterpret_cast<const uint4*>(p + (j * 32 + lane) * 8);
+        if (resid != nullptr) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) ur[j] = *reinterpret_cast<const uint4*>(resid + row * H + (j * 32 + lane) * 8);
+        }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(p + (j * 32 + lane) * 8);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+            const uint32_t wr[4] = {ur[j].x, ur[j].y, ur[j].z, ur[j].w};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const float2 f = unpack_bf16x2(w[h]);
+                float2 f = unpack_bf16x2(w[h]);
+                if (resid != nullptr) {
+                    const float2 g = unpack_bf16x2(wr[h]);
+                    f.x += g.x;
+                    f.y += g.y;
+                }
                 v[j * 8 + 2 * h] = f.x;
                 v[j * 8 + 2 * h + 1] = f.y;
             }
@@ -504,22 +517,23 @@ extern "C" __attribute__((visibility("default"))) int md_timestep_mlp(const floa
     return check_cuda(cudaGetLastError(), "timestep_mlp launch");
 }
 
-extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const void* in, const float* gamma, const float* beta, float eps, void* out, int64_t M,
-                                 int H, cudaStream_t stream) {
+extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const void* in, const void* resid, const float* gamma, const float* beta, float eps, void* out,
+                                 int64_t M, int H, cudaStream_t stream) {
     if (H % 256 != 0 || H > 2048 || H <= 0) { set_last_error("md_layernorm_bf16: H=%d must be a multiple of 256, <= 2048", H); return MD_ERR_ARG; }
     if (M == 0) return MD_OK;
     const int grid = ew_grid(M * 32, 256);
     const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(resid);
     switch (H / 256) {
-        case 1: layernorm_kernel<1><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 2: layernorm_kernel<2><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 3: layernorm_kernel<3><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 4: layernorm_kernel<4><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 5: layernorm_kernel<5><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 6: layernorm_kernel<6><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        case 7: layernorm_kernel<7><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
-        default: layernorm_kernel<8><<<grid, 256, 0, stream>>>(i, gamma, beta, eps, o, M); break;
+        case 1: layernorm_kernel<1><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 2: layernorm_kernel<2><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 3: layernorm_kernel<3><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 4: layernorm_kernel<4><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 5: layernorm_kernel<5><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 6: layernorm_kernel<6><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 7: layernorm_kernel<7><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        default: layernorm_kernel<8><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
     }
     return check_cuda(cudaGetLastError(), "layernorm launch");
 }

@@ -8,7 +8,7 @@
 // tile i overlaps the MMAs of tile i+1.
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..9 = epilogue (TMEM -> registers -> bias / GELU / tanh / residual / pos+time -> global).
+// warps 2..9 = epilogue (TMEM -> registers -> bias / GELU / tanh / pos+time -> swizzled smem slab -> TMA store).
 #include "common.cuh"
 #include "musediff_b200.h"
 
@@ -24,7 +24,6 @@ struct GemmArgs {
     int M, N, K;
     int L;                         // rows per sequence (EPI_POS_TIME)
     const float* bias;             // [N] or nullptr
-    const __nv_bfloat16* resid;    // [M, N]   (MD_EPI_BIAS_RESID)
     const float* pos;              // [L, N]   (MD_EPI_BIAS_POS_TIME)
     const float* temb;             // [M / L, N] (row stride temb_stride; 0 = one row shared by all sequences)
     int temb_stride;
@@ -38,7 +37,9 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+    static constexpr int kSlabBytes = 32 * 128;                 // one epilogue warp's staging slab: 32 rows x 128 B
+    static constexpr int kStagingBytes = 8 * kSlabBytes;
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
 };
 
 template <int EPI>
@@ -48,16 +49,21 @@ MD_DEVINL float epi_act(float v) {
     return v;
 }
 
+// Epilogue data path: TMEM -> registers (thread = output row, 32 consecutive columns per tcgen05.ld) -> bias /
+// activation -> 128B-swizzled shared-memory slab (32 rows x 128 B, one per epilogue warp) -> TMA store.  A direct
+// st.global from the TMEM register layout would touch 32 different 128 B lines per warp instruction (one L1TEX
+// wavefront each); the slab + cp.async.bulk.tensor store costs no LSU wavefronts and clips rows >= M / cols >= N.
 template <int BN, int EPI, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
-    float* sBias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
+    uint8_t* sStage = smem + Cfg::kStages * Cfg::kStageBytes;          // 1024-aligned: kStageBytes is a multiple of 1024
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -74,6 +80,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -141,91 +148,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ew = warp - 2;
         const int q = warp & 3;             // TMEM lane quadrant this warp may access
         const int hsel = ew >> 2;           // which half of the BN columns
-        const int tid_e = threadIdx.x - 64;
+        uint8_t* slab = sStage + ew * Cfg::kSlabBytes;
+        const uint32_t slab_row = smem_u32(slab) + lane * 128;
+        constexpr int kSlabCols = OUT_F32 ? 32 : 64;          // 128 B of output per row
+        constexpr int kSlabs = (BN / 2) / kSlabCols;
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr int kChunks = BN / 2 / 32;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int n0 = n_blk * BN;
-            if (tid_e < BN) {
-                const int n = n0 + tid_e;
-                sBias[acc * BN + tid_e] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.0f;
-            }
-            named_bar_sync(1, kEpiThreads);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            const size_t row_off = (size_t)row * p.N;
+            const int row0 = m_blk * BM + q * 32;
+            const int row = row0 + lane;
             int seq_b = 0, seq_l = 0;
-            if (EPI == MD_EPI_BIAS_POS_TIME && row_ok) { seq_b = row / p.L; seq_l = row - seq_b * p.L; }
+            if (EPI == MD_EPI_BIAS_POS_TIME) {
+                const int rr = row < p.M ? row : p.M - 1;
+                seq_b = rr / p.L;
+                seq_l = rr - seq_b * p.L;
+            }
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-                const int col0 = hsel * (BN / 2) + c * 32;
+            for (int sl = 0; sl < kSlabs; ++sl) {
+                const int col0 = hsel * (BN / 2) + sl * kSlabCols;      // column inside the tile
                 const int n = n0 + col0;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0, r);
-                uint4 res[4];
-                if (EPI == MD_EPI_BIAS_RESID) {
+                if (n >= p.N) break;                                     // warp-uniform
+                float v[kSlabCols];
+                {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0, r);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        res[g] = make_uint4(0, 0, 0, 0);
-                        if (row_ok && n + g * 8 < p.N)
-                            res[g] = *reinterpret_cast<const uint4*>(p.resid + row_off + n + g * 8);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (!OUT_F32) {
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0 + 32, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[(kSlabCols - 32) + j] = __uint_as_float(r[j]);
                     }
                 }
-                tc_wait_ld();
-                float v[32];
-                const float* bias_s = sBias + acc * BN + col0;
+                if (p.bias != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[j];
-                if (EPI == MD_EPI_BIAS_RESID) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t w[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float2 f = unpack_bf16x2(w[h]);
-                            v[g * 8 + 2 * h] += f.x;
-                            v[g * 8 + 2 * h + 1] += f.y;
-                        }
+                    for (int g = 0; g < kSlabCols / 4; ++g) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n + g * 4 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 4));
+                        v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
                     }
                 }
                 if (EPI == MD_EPI_BIAS_POS_TIME) {
-                    if (row_ok) {
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            if (n + g * 4 < p.N) {
-                                const float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)seq_l * p.N + n + g * 4);
-                                const float4 b = *reinterpret_cast<const float4*>(p.temb + (size_t)seq_b * p.temb_stride + n + g * 4);
-                                v[g * 4 + 0] += a.x + b.x;
-                                v[g * 4 + 1] += a.y + b.y;
-                                v[g * 4 + 2] += a.z + b.z;
-                                v[g * 4 + 3] += a.w + b.w;
-                            }
+                    for (int g = 0; g < kSlabCols / 4; ++g) {
+                        if (n + g * 4 < p.N) {
+                            const float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)seq_l * p.N + n + g * 4);
+                            const float4 b = *reinterpret_cast<const float4*>(p.temb + (size_t)seq_b * p.temb_stride + n + g * 4);
+                            v[g * 4 + 0] += a.x + b.x;
+                            v[g * 4 + 1] += a.y + b.y;
+                            v[g * 4 + 2] += a.z + b.z;
+                            v[g * 4 + 3] += a.w + b.w;
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = epi_act<EPI>(v[j]);
-                if (row_ok) {
+                for (int j = 0; j < kSlabCols; ++j) v[j] = epi_act<EPI>(v[j]);
+                // the previous TMA store out of this slab must have finished reading shared memory
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {       // 8 x 16 B chunks per 128 B row, 128B swizzle: chunk ^= row % 8
+                    uint4 u;
                     if (OUT_F32) {
-                        float* o = reinterpret_cast<float*>(p.out) + row_off + n;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            if (n + g * 4 < p.N)
-                                *reinterpret_cast<float4*>(o + g * 4) =
-                                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        u = make_uint4(__float_as_uint(v[c * 4 + 0]), __float_as_uint(v[c * 4 + 1]),
+                                       __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3]));
                     } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (n + g * 8 < p.N)
-                                *reinterpret_cast<uint4*>(o + g * 8) =
-                                    make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                               pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                        u = make_uint4(pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                                       pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
                     }
+                    const uint32_t addr = slab_row + ((c ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                                 : "memory");
+                }
+                fence_proxy_async_smem();           // generic-proxy writes -> visible to the async (TMA) proxy
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, slab, n, row0);
+                    tma_store_commit();
                 }
             }
             tc_fence_before();
@@ -233,6 +238,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) tma_store_wait_read<0>();
+        // global visibility of the bulk stores is guaranteed at kernel completion (stream order)
     }
     __syncwarp();
     tc_fence_before();
@@ -259,16 +266,16 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle.
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+// 2-D row-major [rows, cols] tensor (bf16 or fp32), box = [box_rows, box_cols] with box_cols * elem = 128 B, 128B swizzle.
+int make_tmap_2d(CUtensorMap* tm, const void* base, int is_f32, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {row_stride_elems * 2};
+    cuuint64_t gstr[1] = {row_stride_elems * (is_f32 ? 4 : 2)};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -312,7 +319,8 @@ int num_sms() {
 }
 
 template <int BN, int EPI, bool OUT_F32>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
+                       cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_kernel<BN, EPI, OUT_F32>;
     static bool attr_set = false;
@@ -324,18 +332,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int n_tiles = (args.N + BN - 1) / BN, m_tiles = (args.M + BM - 1) / BM;
     const int grid = min(n_tiles * m_tiles, num_sms());
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, args);
     return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
 template <int BN, bool OUT_F32>
-static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t s) {
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& a,
+                        cudaStream_t s) {
     switch (epi) {
-        case MD_EPI_BIAS: return launch_gemm<BN, MD_EPI_BIAS, OUT_F32>(tmA, tmB, a, s);
-        case MD_EPI_BIAS_GELU: return launch_gemm<BN, MD_EPI_BIAS_GELU, OUT_F32>(tmA, tmB, a, s);
-        case MD_EPI_BIAS_TANH: return launch_gemm<BN, MD_EPI_BIAS_TANH, OUT_F32>(tmA, tmB, a, s);
-        case MD_EPI_BIAS_RESID: return launch_gemm<BN, MD_EPI_BIAS_RESID, OUT_F32>(tmA, tmB, a, s);
-        case MD_EPI_BIAS_POS_TIME: return launch_gemm<BN, MD_EPI_BIAS_POS_TIME, OUT_F32>(tmA, tmB, a, s);
+        case MD_EPI_BIAS: return launch_gemm<BN, MD_EPI_BIAS, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_GELU: return launch_gemm<BN, MD_EPI_BIAS_GELU, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_TANH: return launch_gemm<BN, MD_EPI_BIAS_TANH, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_POS_TIME: return launch_gemm<BN, MD_EPI_BIAS_POS_TIME, OUT_F32>(tmA, tmB, tmC, a, s);
     }
     set_last_error("md_linear_bf16: unknown epilogue %d", epi);
     return MD_ERR_ARG;
@@ -346,24 +354,24 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 using namespace md;
 
 extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int epilogue,
-                              int out_is_f32, const void* resid, const float* pos, const float* temb, int temb_stride,
-                              int L, cudaStream_t stream) {
+                              int out_is_f32, const float* pos, const float* temb, int temb_stride, int L,
+                              cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0) { set_last_error("md_linear_bf16: empty problem M=%d N=%d K=%d", M, N, K); return MD_ERR_ARG; }
     if (K % 8 != 0 || N % 8 != 0) { set_last_error("md_linear_bf16: K and N must be multiples of 8 (K=%d N=%d)", K, N); return MD_ERR_ARG; }
-    if (epilogue == MD_EPI_BIAS_RESID && resid == nullptr) { set_last_error("md_linear_bf16: residual pointer missing"); return MD_ERR_ARG; }
     if (epilogue == MD_EPI_BIAS_POS_TIME && (pos == nullptr || temb == nullptr || L <= 0 || M % L != 0)) {
         set_last_error("md_linear_bf16: pos/time epilogue needs pos, temb and L dividing M");
         return MD_ERR_ARG;
     }
     const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
-    CUtensorMap tmA, tmB;
-    if (int e = make_tmap_bf16_2d(&tmA, A, M, K, K, BM, BK)) return e;
-    if (int e = make_tmap_bf16_2d(&tmB, W, N, K, K, BN, BK)) return e;
+    CUtensorMap tmA, tmB, tmC;
+    if (int e = make_tmap_2d(&tmA, A, 0, M, K, K, BM, BK)) return e;
+    if (int e = make_tmap_2d(&tmB, W, 0, N, K, K, BN, BK)) return e;
+    if (int e = make_tmap_2d(&tmC, out, out_is_f32, M, N, N, 32, out_is_f32 ? 32 : 64)) return e;
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
-    a.bias = bias; a.resid = reinterpret_cast<const __nv_bfloat16*>(resid); a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
-    if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, a, stream)
-                                     : dispatch_epi<256, false>(epilogue, tmA, tmB, a, stream);
-    return out_is_f32 ? dispatch_epi<128, true>(epilogue, tmA, tmB, a, stream)
-                      : dispatch_epi<128, false>(epilogue, tmA, tmB, a, stream);
+    a.bias = bias; a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
+    if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, tmC, a, stream)
+                                     : dispatch_epi<256, false>(epilogue, tmA, tmB, tmC, a, stream);
+    return out_is_f32 ? dispatch_epi<128, true>(epilogue, tmA, tmB, tmC, a, stream)
+                      : dispatch_epi<128, false>(epilogue, tmA, tmB, tmC, a, stream);
 }

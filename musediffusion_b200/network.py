@@ -1,5 +1,5 @@
 """TransformerNetModel — host-side mirror of MuseDiffusion/models/network.py:20-158 whose forward runs on the
-hand-written sm_100a kernels (tcgen05 GEMMs + fused attention + vectorised LayerNorm) through the C-ABI library.
+hand-written sm_100a kernels (tcgen05 GEMMs + fused attention + vectorised residual-LayerNorm) through the C-ABI library.
 
 The module tree reproduces the reference's parameter names exactly (211 state-dict keys at the base config,
 SURVEY.md section 5), so `load_state_dict` of a reference checkpoint works unchanged.  The encoder the reference
@@ -260,11 +260,11 @@ class TransformerNetModel(nn.Module):
         for ly in pk.layers:
             ops.linear(h, ly.wqkv, ly.bqkv, E.EPI_BIAS, out=ws.qkv)
             ops.attention(ws.qkv, B, L, pk.NH, out=h1)                       # ctx -> h1 buffer
-            ops.linear(h1, ly.wo, ly.bo, E.EPI_BIAS_RESID, resid=h, out=pre)
-            ops.layernorm(pre, ly.g1, ly.b1, pk.eps, out=h1)
+            ops.linear(h1, ly.wo, ly.bo, E.EPI_BIAS, out=pre)
+            ops.layernorm(pre, ly.g1, ly.b1, pk.eps, resid=h, out=h1)        # LN(dense(ctx) + h)
             ops.linear(h1, ly.w1, ly.bi, E.EPI_BIAS_GELU, out=ws.mid)
-            ops.linear(ws.mid, ly.w2, ly.b2, E.EPI_BIAS_RESID, resid=h1, out=pre)
-            ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, out=h)
+            ops.linear(ws.mid, ly.w2, ly.b2, E.EPI_BIAS, out=pre)
+            ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, resid=h1, out=h)       # LN(dense(mid) + h1)
         ops.linear(h, pk.dn1_w, pk.dn1_b, E.EPI_BIAS_TANH, out=h1)
         if out is None:
             out = torch.empty((M, D), dtype=torch.float32, device=x.device)

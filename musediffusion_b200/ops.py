@@ -112,18 +112,19 @@ def timestep_mlp(t, W0, b0, W2, b2):
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None):
+def layernorm(x, gamma, beta, eps, resid=None, out=None):
+    """LayerNorm(x + resid) (resid optional), bf16 in/out."""
     assert x.dtype == BF16 and x.is_contiguous()
+    assert resid is None or (resid.dtype == BF16 and resid.is_contiguous() and resid.shape == x.shape)
     H = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
-    call("md_layernorm_bf16", _p(x), _p(gamma), _p(beta), float(eps), _p(out), x.numel() // H, H, _stream())
+    call("md_layernorm_bf16", _p(x), _p(resid), _p(gamma), _p(beta), float(eps), _p(out), x.numel() // H, H, _stream())
     return out
 
 
 # ------------------------------------------------------------------------------------------------ contractions
-def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, resid=None, pos=None, temb=None, temb_stride=0, L=0,
-           out=None):
+def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, pos=None, temb=None, temb_stride=0, L=0, out=None):
     """out[M,N] = epi(A[M,K] @ W[N,K]^T + bias)."""
     assert A.dtype == BF16 and W.dtype == BF16 and A.is_contiguous() and W.is_contiguous()
     M, K = A.shape
@@ -132,7 +133,7 @@ def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, resid=None, pos=N
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     call("md_linear_bf16", _p(A), _p(W), _p(bias), _p(out), M, N, K, epilogue, int(out.dtype == torch.float32),
-         _p(resid), _p(pos), _p(temb), temb_stride, L, _stream(), detail="%dx%dx%d epi=%d" % (M, N, K, epilogue))
+         _p(pos), _p(temb), temb_stride, L, _stream(), detail="%dx%dx%d epi=%d" % (M, N, K, epilogue))
     return out
 
 
