@@ -31,7 +31,7 @@ constexpr int ATT_BKV = 128;       // keys per K/V stage
 constexpr int ATT_DH = 64;
 constexpr int ATT_STAGES = 3;
 constexpr int kAttThreads = 384;
-constexpr int kRegsProducer = 80, kRegsSoftmax = 216;   // 128*80 + 256*216 = 65536
+constexpr int kRegsProducer = 56, kRegsSoftmax = 224;   // 128*56 + 256*224 = 64512 = 384 threads x 168 regs at launch (the CTA pool)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;   // TMEM columns

@@ -80,14 +80,14 @@ MD_DEVINL float norm_quantile(float p) {
         const bool upper = p > 0.5f;
         const float pp = upper ? 1.0f - p : p;
         const float q = sqrtf(-2.0f * logf(fmaxf(pp, 1e-30f)));
-        const float x = (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) /
-                        ((((d0 * q + d1) * q + d2) * q + d3) * q + 1.0f);
+        const float x = __fdividef((((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5),
+                                   ((((d0 * q + d1) * q + d2) * q + d3) * q + 1.0f));
         return upper ? -x : x;
     }
     const float q = p - 0.5f;
     const float r = q * q;
-    return (((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q /
-           (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1.0f);
+    return __fdividef((((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q,
+                      (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1.0f));
 }
 struct NoiseGen {
     uint2 key;
@@ -119,6 +119,32 @@ struct NoiseGen {
         return n;
     }
 };
+
+// flat float4 index -> (token, first element inside the token, sequence).  64-bit divisions cost ~100 instructions
+// each on the GPU, so the common power-of-two D goes through shifts and the sequence index through a 32-bit divide.
+struct TokPos {
+    int64_t tok;
+    int d, b;
+};
+MD_DEVINL TokPos tok_pos(int64_t i, int vec_per_tok, int vshift, int L) {
+    TokPos r;
+    if (vshift >= 0) {
+        r.tok = i >> vshift;
+        r.d = (int)(i & (vec_per_tok - 1)) << 2;
+    } else {
+        r.tok = i / vec_per_tok;
+        r.d = (int)(i - r.tok * vec_per_tok) << 2;
+    }
+    r.b = (int)((uint32_t)r.tok / (uint32_t)L);     // host guarantees tokens < 2^31
+    return r;
+}
+static int vec_shift(int D) {
+    const int v = D >> 2;
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
+}
 
 MD_DEVINL float4 ld_stream_f4(const float* p) {
     float4 v;
@@ -152,7 +178,7 @@ struct StepArgs {
     float* pred_out;         // optional: processed pred_xstart
     float* mean_out;         // optional: posterior mean ("greedy_mean")
     int64_t seq_offset;
-    int B, L, D;
+    int B, L, D, vshift;
     float eta;
     int clip;
     NoiseGen rng;
@@ -166,10 +192,10 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
     const int vec_per_tok = a.D >> 2;
     const int64_t total = (int64_t)a.B * a.L * vec_per_tok;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t tok = i / vec_per_tok;
-        const int d = (int)(i - tok * vec_per_tok) << 2;
-        const int b = (int)(tok / a.L);
-        const int t = a.t[b * a.t_stride];
+        const TokPos tp = tok_pos(i, vec_per_tok, a.vshift, a.L);
+        const int64_t tok = tp.tok;
+        const int d = tp.d;
+        const int t = a.t[tp.b * a.t_stride];
         const int64_t off = tok * a.D + d;
         const float4 x = ld_stream_f4(a.x_t + off);
         float4 pr;
@@ -234,12 +260,12 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-xstart_from_eps_kernel(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L, int D, SchedRef s) {
+xstart_from_eps_kernel(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L, int D,
+                       int vshift, SchedRef s) {
     const int vec_per_tok = D >> 2;
     const int64_t total = (int64_t)B * L * vec_per_tok;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t tok = i / vec_per_tok;
-        const int tt = t[(tok / L) * t_stride];
+        const int tt = t[tok_pos(i, vec_per_tok, vshift, L).b * t_stride];
         const float sr = s.get(TAB_SR, tt), srm1 = s.get(TAB_SRM1, tt);
         const float4 x = ld_stream_f4(x_t + i * 4), e = ld_stream_f4(eps + i * 4);
         float4 o;
@@ -261,7 +287,7 @@ struct QSampleArgs {
     float* out;
     __nv_bfloat16* out_bf16;
     int64_t seq_offset;
-    int B, L, D;
+    int B, L, D, vshift;
     NoiseGen rng;
     const float* sched_dev;
     int T;
@@ -270,10 +296,11 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const QSampleArgs a) {
     const int vec_per_tok = a.D >> 2;
     const int64_t total = (int64_t)a.B * a.L * vec_per_tok;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t tok = i / vec_per_tok;
-        const int d = (int)(i - tok * vec_per_tok) << 2;
+        const TokPos tp = tok_pos(i, vec_per_tok, a.vshift, a.L);
+        const int64_t tok = tp.tok;
+        const int d = tp.d;
         const int64_t off = tok * a.D + d;
-        const int t = a.t ? a.t[(tok / a.L) * a.t_stride] : -1;
+        const int t = a.t ? a.t[tp.b * a.t_stride] : -1;
         const float4 x = ld_stream_f4(a.x0 + off);
         float4 n;
         if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
@@ -551,12 +578,13 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     if (mask != nullptr && x_start == nullptr) { set_last_error("md_posterior_step: mask needs x_start"); return MD_ERR_ARG; }
     if (mode != MD_STEP_DDPM && mode != MD_STEP_DDIM) { set_last_error("md_posterior_step: bad mode %d", mode); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
+    if ((int64_t)B * L >= (int64_t)1 << 31) { set_last_error("md_posterior_step: more than 2^31 tokens"); return MD_ERR_ARG; }
     StepArgs a;
     a.x_t = x_t; a.idx = idx; a.pred_in = pred_in; a.E = E; a.noise = noise; a.t = t; a.t_stride = t_stride ? 1 : 0;
     a.mask = mask; a.pred_out = pred_out; a.mean_out = mean_out;
     a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride; a.x_start = x_start; a.x_out = x_out;
     a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
-    a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref();
+    a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref(); a.vshift = vec_shift(D);
     const int grid = ew_grid((int64_t)B * L * (D / 4), 256);
     if (mode == MD_STEP_DDPM) posterior_step_kernel<MD_STEP_DDPM><<<grid, 256, 0, stream>>>(a);
     else posterior_step_kernel<MD_STEP_DDIM><<<grid, 256, 0, stream>>>(a);
@@ -568,7 +596,7 @@ extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const f
     if (g_sched_T == 0) { set_last_error("md_xstart_from_eps: md_set_schedule has not been called"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_xstart_from_eps: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
-    xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, t_stride ? 1 : 0, out, B, L, D, sched_ref());
+    xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, t_stride ? 1 : 0, out, B, L, D, vec_shift(D), sched_ref());
     return check_cuda(cudaGetLastError(), "xstart_from_eps launch");
 }
 
@@ -581,7 +609,7 @@ extern "C" __attribute__((visibility("default"))) int md_q_sample(const float* x
     QSampleArgs a;
     a.x0 = x0; a.noise = noise; a.t = t; a.t_stride = t_stride ? 1 : 0; a.mask = mask; a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride;
     a.out = out; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
-    a.rng.init(seed, step_counter, 0.0f); a.sched_dev = g_sched_dev; a.T = g_sched_T;
+    a.rng.init(seed, step_counter, 0.0f); a.sched_dev = g_sched_dev; a.T = g_sched_T; a.vshift = vec_shift(D);
     q_sample_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "q_sample launch");
 }
