@@ -31,7 +31,7 @@ constexpr int ATT_BKV = 128;       // keys per K/V stage
 constexpr int ATT_DH = 64;
 constexpr int ATT_STAGES = 3;
 constexpr int kAttThreads = 384;
-constexpr int kRegsProducer = 56, kRegsSoftmax = 224;   // 128*56 + 256*224 = 64512 = 384 threads x 168 regs at launch (the CTA pool)
+constexpr int kRegsProducer = 72, kRegsSoftmax = 216;   // 128*72 + 256*216 = 64512 = 384 threads x 168 regs at launch (the CTA pool)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;   // TMEM columns
@@ -117,32 +117,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     if (warp == 0) {
-        // =========================================================== TMA producer
-        if (lane == 0) {
+        // =========================================================== TMA producer (whole warp, elected issue)
+        {
             uint32_t wcnt = 0, kcnt = 0;
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
                 const int qt0 = wk.pair * 2;
                 const int n_active = (qt0 + 1 < a.n_qtiles) ? 2 : 1;
                 mbar_wait(q_empty, (wcnt & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, n_active * ATT_TILE_BYTES);
+                mbar_arrive_expect_tx_w(q_full, n_active * ATT_TILE_BYTES);
                 for (int x = 0; x < n_active; ++x)
-                    tma_load_3d(sQ + x * ATT_TILE_BYTES, &tmQKV, q_full, wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
+                    tma_load_3d_w(sQ + x * ATT_TILE_BYTES, &tmQKV, q_full, wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
                 for (int j = 0; j < a.n_kv; ++j, ++kcnt) {
                     const int st = kcnt % ATT_STAGES;
                     const uint32_t ph = (kcnt / ATT_STAGES) & 1;
                     mbar_wait(&k_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
-                    tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &k_full[st], H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
+                    mbar_arrive_expect_tx_w(&k_full[st], ATT_TILE_BYTES);
+                    tma_load_3d_w(sK + st * ATT_TILE_BYTES, &tmQKV, &k_full[st], H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
                     mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
-                    tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &v_full[st], 2 * H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
+                    mbar_arrive_expect_tx_w(&v_full[st], ATT_TILE_BYTES);
+                    tma_load_3d_w(sV + st * ATT_TILE_BYTES, &tmQKV, &v_full[st], 2 * H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
                 }
             }
         }
     } else if (warp == 1) {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
+        // =========================================================== MMA issuer (whole warp runs, one elected lane issues)
+        {
             constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, ATT_DH, 1);   // B (= V) is MN-major
             const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
@@ -153,15 +153,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             auto issue_qk = [&](int x, int st) {
                 const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
                 const uint64_t kd = make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
-#pragma unroll 1
-                for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(tS[x], qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-                tc_commit(&s_full[x]);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_ss_w(tS[x], qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+                tc_commit_w(&s_full[x]);
             };
             auto issue_pv = [&](int x, int st, bool accumulate) {
                 const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
-#pragma unroll 1
+#pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k)   // 16 keys = 8 packed TMEM columns of P, 2048 B of V rows
-                    umma_ts(tO[x], tS[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+                    umma_ts_w(tO[x], tS[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
             };
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
@@ -174,7 +174,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
 #pragma unroll
                     for (int x = 0; x < 2; ++x)
                         if (x < n_active) issue_qk(x, st);
-                    tc_commit(&k_empty[st]);
+                    tc_commit_w(&k_empty[st]);
                 }
                 for (int j = 0; j < a.n_kv; ++j) {
                     const int st = (kcnt + j) % ATT_STAGES;
@@ -192,13 +192,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         ++pcnt[x];
                         tc_fence_after();
                         issue_pv(x, st, j > 0);
-                        if (!has_next) { tc_commit(&o_full[x]); ++ocnt[x]; }
+                        if (!has_next) { tc_commit_w(&o_full[x]); ++ocnt[x]; }
                         if (has_next) issue_qk(x, st_n);     // S(j+1) of this tile while the other tile's softmax runs
                     }
-                    tc_commit(&v_empty[st]);
-                    if (has_next) tc_commit(&k_empty[st_n]);
+                    tc_commit_w(&v_empty[st]);
+                    if (has_next) tc_commit_w(&k_empty[st_n]);
                 }
-                tc_commit(q_empty);
+                tc_commit_w(q_empty);
                 kcnt += a.n_kv;
             }
         }

@@ -98,50 +98,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-                }
+        // ------------------------------------------------ TMA producer (whole warp, elected issue)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_2d_w(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                tma_load_2d_w(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ------------------------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues)
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
-                    const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+                const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+                const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // +32 bytes per UMMA_K step inside the 128B swizzle atom  (encoded >> 4)
-                        umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    tc_commit(&empty_bar[stage]);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // +32 bytes per UMMA_K step inside the 128B swizzle atom  (encoded >> 4)
+                    umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                 }
-                tc_commit(&tfull_bar[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                tc_commit_w(&empty_bar[stage]);
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
+            tc_commit_w(&tfull_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else {
         // ------------------------------------------------ epilogue (8 warps)
