@@ -7,7 +7,7 @@
 // materialises [B, 12, L, L] fp32 scores in HBM.  Here the scores never leave the SM:
 //   * S = Q K^T by tcgen05.mma (SS) into TMEM, one 128x128 fp32 tile per Q tile,
 //   * each softmax thread owns one row of S (tcgen05.ld 32x32b), keeps the running max / sum in registers, writes
-//     P = exp2(..) as packed bf16 back over S in TMEM,
+//     P = exp2(..) as packed bf16 into its own TMEM columns,
 //   * O += P V by tcgen05.mma with A = P from TMEM (TS form), B = V tile (MN-major, 128B swizzle) from shared memory,
 //   * O is rescaled lazily in TMEM only when the row max grew by more than 2^8 (exact after final normalisation).
 // One persistent CTA per SM works on TWO 128-row Q tiles of the same (b, h) so the tensor pipe computes S for one
@@ -34,7 +34,9 @@ constexpr int kAttThreads = 384;
 constexpr int kRegsProducer = 72, kRegsSoftmax = 216;   // 128*72 + 256*216 = 64512 = 384 threads x 168 regs at launch (the CTA pool)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;   // TMEM columns
+// TMEM columns (all 512 used): S and P have separate homes so that S(j+1) = Q K^T can be issued as soon as the softmax
+// warpgroup has READ S(j) into registers — the tensor pipe's latency leaves the softmax critical path.
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
@@ -84,7 +86,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     uint64_t* p_full = s_full + 2;             // [2]
     uint64_t* o_full = p_full + 2;             // [2]
     uint64_t* o_empty = o_full + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+    uint64_t* s_free = o_empty + 2;            // [2] softmax has read S into registers -> next Q K^T may overwrite it
+    uint64_t* p_free = s_free + 2;             // [2] P V of the previous block retired -> P / O may be rewritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -105,6 +109,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             mbar_init(&p_full[x], 128);
             mbar_init(&o_full[x], 1);
             mbar_init(&o_empty[x], 128);
+            mbar_init(&s_free[x], 128);
+            mbar_init(&p_free[x], 1);
         }
         fence_barrier_init();
     }
@@ -147,10 +153,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, ATT_DH, 1);   // B (= V) is MN-major
             const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
             const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
+            const uint32_t tP[2] = {tmem_base + TM_P0, tmem_base + TM_P1};
             uint32_t wcnt = 0, kcnt = 0;
-            uint32_t pcnt[2] = {0, 0};   // completed P tiles per Q tile (phase of p_full)
+            uint32_t pcnt[2] = {0, 0};   // P tiles consumed per Q tile (phase of p_full)
             uint32_t ocnt[2] = {0, 0};   // work items per Q tile (phase of o_empty)
+            uint32_t qcnt[2] = {0, 0};   // Q K^T issued per Q tile (phase of s_free)
             auto issue_qk = [&](int x, int st) {
+                // S_x may be overwritten once the softmax warpgroup has read the previous S_x into registers
+                if (qcnt[x] > 0) mbar_wait(&s_free[x], (qcnt[x] - 1) & 1);
+                ++qcnt[x];
+                tc_fence_after();
                 const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
                 const uint64_t kd = make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
 #pragma unroll
@@ -161,7 +173,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k)   // 16 keys = 8 packed TMEM columns of P, 2048 B of V rows
-                    umma_ts_w(tO[x], tS[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+                    umma_ts_w(tO[x], tP[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
             };
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
@@ -170,7 +182,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 {   // S(0) for both tiles
                     const int st = kcnt % ATT_STAGES;
                     mbar_wait(&k_full[st], (kcnt / ATT_STAGES) & 1);
-                    tc_fence_after();
 #pragma unroll
                     for (int x = 0; x < 2; ++x)
                         if (x < n_active) issue_qk(x, st);
@@ -182,8 +193,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     const int st_n = (kcnt + j + 1) % ATT_STAGES;
                     const uint32_t ph_n = ((kcnt + j + 1) / ATT_STAGES) & 1;
                     const bool has_next = (j + 1 < a.n_kv);
+                    if (has_next) {
+                        // S(j+1) for both tiles: needs only K[j+1] and the softmax warpgroup's READ of S(j)
+                        mbar_wait(&k_full[st_n], ph_n);
+#pragma unroll
+                        for (int x = 0; x < 2; ++x)
+                            if (x < n_active) issue_qk(x, st_n);
+                        tc_commit_w(&k_empty[st_n]);
+                    }
                     mbar_wait(&v_full[st], ph);
-                    if (has_next) mbar_wait(&k_full[st_n], ph_n);
 #pragma unroll
                     for (int x = 0; x < 2; ++x) {
                         if (x >= n_active) continue;
@@ -192,11 +210,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         ++pcnt[x];
                         tc_fence_after();
                         issue_pv(x, st, j > 0);
-                        if (!has_next) { tc_commit_w(&o_full[x]); ++ocnt[x]; }
-                        if (has_next) issue_qk(x, st_n);     // S(j+1) of this tile while the other tile's softmax runs
+                        if (has_next) tc_commit_w(&p_free[x]);
+                        else { tc_commit_w(&o_full[x]); ++ocnt[x]; }
                     }
                     tc_commit_w(&v_empty[st]);
-                    if (has_next) tc_commit_w(&k_empty[st_n]);
                 }
                 tc_commit_w(q_empty);
                 kcnt += a.n_kv;
@@ -213,8 +230,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         const int r = quad * 32 + lane;         // row inside the Q tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0) + lane_addr;
+        const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0) + lane_addr;
         const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0) + lane_addr;
-        uint32_t scnt = 0, ocnt = 0;
+        uint32_t scnt = 0, ocnt = 0, fcnt = 0;
         for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
             const Work wk = decode_work(w, a);
             const int qt = wk.pair * 2 + x;
@@ -234,6 +252,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) tmem_ld32(tS + 32 * g, s[g]);
                 tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&s_free[x]);               // S is in registers: the next Q K^T may overwrite it
                 const int valid = a.L - j * ATT_BKV;   // keys in this block that exist
                 if (valid < ATT_BKV) {
 #pragma unroll
@@ -257,6 +277,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 if (j == 0) {
                     m_used = mb;
                 } else {
+                    mbar_wait(&p_free[x], fcnt & 1);   // P V of block j-1 retired: O and P may be touched
+                    ++fcnt;
+                    tc_fence_after();
                     const bool need = mb > m_used + kRescaleThreshold;
                     if (__any_sync(0xffffffffu, need)) {
                         // lazy rescale of the running output (and sum) held in TMEM
@@ -288,7 +311,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         if (c & 1) { acc2 += p0; acc3 += p1; } else { acc0 += p0; acc1 += p1; }
                         pk[c] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st16(tS + g * 16, pk);    // P overwrites the first 64 columns of S (row already in registers)
+                    tmem_st16(tP + g * 16, pk);
                 }
                 turn_pass(x);                                                   // hand the MUFU pipe to the other tile
                 l_sum += (acc0 + acc1) + (acc2 + acc3);
