@@ -13,11 +13,13 @@
 // One persistent CTA per SM works on TWO 128-row Q tiles of the same (b, h) so the tensor pipe computes S for one
 // tile while the other tile's softmax runs, and both tiles share every K/V stage brought in by TMA.
 //
-// Roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0: TMA producer, warp 1: TMEM owner + single-thread MMA
-// issuer, warps 2-3: idle}, warpgroup 1 = softmax/correction/epilogue for Q tile 0, warpgroup 2 = same for Q tile 1.
+// Roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0: TMA producer, warp 1: TMEM owner + MMA issuer of Q
+// tile 0, warp 2: MMA issuer of Q tile 1, warp 3: idle}, warpgroup 1 = softmax/correction/epilogue for Q tile 0, warpgroup 2 = same for Q tile 1.
 // setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (a full S row lives in registers), and a
 // pair of named barriers makes the two softmax warpgroups take turns on the exp2 (MUFU) phase: at head dim 64 the
 // MUFU pipe, not the tensor pipe, is the binding unit, so its phases must never idle or overlap.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "musediff_b200.h"
 
@@ -59,15 +61,20 @@ MD_DEVINL Work decode_work(int w, const AttArgs& a) {
     return r;
 }
 
+template <bool kTurns>
 MD_DEVINL void turn_wait(int x) {
+    if (!kTurns) return;
     if (x == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
     else asm volatile("bar.sync 3, 256;" ::: "memory");
 }
+template <bool kTurns>
 MD_DEVINL void turn_pass(int x) {
+    if (!kTurns) return;
     if (x == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
     else asm volatile("bar.arrive 2, 256;" ::: "memory");
 }
 
+template <bool kTurns, int kPoly>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -97,12 +104,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
+        mbar_init(q_empty, 2);                 // both MMA warps (one per Q tile) release the shared stages
         for (int s = 0; s < ATT_STAGES; ++s) {
             mbar_init(&k_full[s], 1);
-            mbar_init(&k_empty[s], 1);
+            mbar_init(&k_empty[s], 2);
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1);
+            mbar_init(&v_empty[s], 2);
         }
         for (int x = 0; x < 2; ++x) {
             mbar_init(&s_full[x], 1);
@@ -146,72 +153,62 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================================================== MMA issuer (whole warp runs, one elected lane issues)
-        {
+    } else {
+        // =========================================================== MMA issuers: warp 1 -> Q tile 0, warp 2 -> Q tile 1
+        // (whole warp runs the loop, one elected lane issues).  One issuing warp per tile: the issue stream of a
+        // single warp (waits, descriptor moves, 24 small MMAs per key block) was measured to be the critical path.
+        if (warp == 1 || warp == 2) {
+            const int x = warp - 1;
             constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, ATT_DH, 1);   // B (= V) is MN-major
-            const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
-            const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
-            const uint32_t tP[2] = {tmem_base + TM_P0, tmem_base + TM_P1};
+            const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0);
+            const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0);
+            const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0);
+            const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
             uint32_t wcnt = 0, kcnt = 0;
-            uint32_t pcnt[2] = {0, 0};   // P tiles consumed per Q tile (phase of p_full)
-            uint32_t ocnt[2] = {0, 0};   // work items per Q tile (phase of o_empty)
-            uint32_t qcnt[2] = {0, 0};   // Q K^T issued per Q tile (phase of s_free)
-            auto issue_qk = [&](int x, int st) {
-                // S_x may be overwritten once the softmax warpgroup has read the previous S_x into registers
-                if (qcnt[x] > 0) mbar_wait(&s_free[x], (qcnt[x] - 1) & 1);
-                ++qcnt[x];
-                tc_fence_after();
-                const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
-                const uint64_t kd = make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < ATT_DH / 16; ++k) umma_ss_w(tS[x], qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-                tc_commit_w(&s_full[x]);
-            };
-            auto issue_pv = [&](int x, int st, bool accumulate) {
-                const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < ATT_BKV / 16; ++k)   // 16 keys = 8 packed TMEM columns of P, 2048 B of V rows
-                    umma_ts_w(tO[x], tP[x] + 8 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-            };
+            uint32_t pcnt = 0;   // P tiles consumed (phase of p_full)
+            uint32_t ocnt = 0;   // work items (phase of o_empty)
+            uint32_t qcnt = 0;   // Q K^T issued (phase of s_free)
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
-                const int n_active = (wk.pair * 2 + 1 < a.n_qtiles) ? 2 : 1;
+                const bool active = (wk.pair * 2 + x < a.n_qtiles);
                 mbar_wait(q_full, wcnt & 1);
-                {   // S(0) for both tiles
+                {   // S(0)
                     const int st = kcnt % ATT_STAGES;
                     mbar_wait(&k_full[st], (kcnt / ATT_STAGES) & 1);
-#pragma unroll
-                    for (int x = 0; x < 2; ++x)
-                        if (x < n_active) issue_qk(x, st);
+                    if (active) {
+                        if (qcnt > 0) mbar_wait(&s_free[x], (qcnt - 1) & 1);
+                        ++qcnt;
+                        tc_fence_after();
+                        umma_qk64_commit_w(tS, qd, make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES)), idesc_qk, &s_full[x]);
+                    }
                     tc_commit_w(&k_empty[st]);
                 }
                 for (int j = 0; j < a.n_kv; ++j) {
                     const int st = (kcnt + j) % ATT_STAGES;
                     const uint32_t ph = ((kcnt + j) / ATT_STAGES) & 1;
-                    const int st_n = (kcnt + j + 1) % ATT_STAGES;
-                    const uint32_t ph_n = ((kcnt + j + 1) / ATT_STAGES) & 1;
                     const bool has_next = (j + 1 < a.n_kv);
                     if (has_next) {
-                        // S(j+1) for both tiles: needs only K[j+1] and the softmax warpgroup's READ of S(j)
-                        mbar_wait(&k_full[st_n], ph_n);
-#pragma unroll
-                        for (int x = 0; x < 2; ++x)
-                            if (x < n_active) issue_qk(x, st_n);
+                        // S(j+1): needs only K[j+1] and the softmax warpgroup's READ of S(j)
+                        const int st_n = (kcnt + j + 1) % ATT_STAGES;
+                        mbar_wait(&k_full[st_n], ((kcnt + j + 1) / ATT_STAGES) & 1);
+                        if (active) {
+                            mbar_wait(&s_free[x], (qcnt - 1) & 1);
+                            ++qcnt;
+                            tc_fence_after();
+                            umma_qk64_commit_w(tS, qd, make_sdesc_sw128(smem_u32(sK + st_n * ATT_TILE_BYTES)), idesc_qk, &s_full[x]);
+                        }
                         tc_commit_w(&k_empty[st_n]);
                     }
                     mbar_wait(&v_full[st], ph);
-#pragma unroll
-                    for (int x = 0; x < 2; ++x) {
-                        if (x >= n_active) continue;
-                        if (j == 0) mbar_wait(&o_empty[x], (ocnt[x] & 1) ^ 1);   // previous item's O drained
-                        mbar_wait(&p_full[x], pcnt[x] & 1);
-                        ++pcnt[x];
+                    if (active) {
+                        if (j == 0) mbar_wait(&o_empty[x], (ocnt & 1) ^ 1);   // previous item's O drained
+                        mbar_wait(&p_full[x], pcnt & 1);
+                        ++pcnt;
                         tc_fence_after();
-                        issue_pv(x, st, j > 0);
-                        if (has_next) tc_commit_w(&p_free[x]);
-                        else { tc_commit_w(&o_full[x]); ++ocnt[x]; }
+                        umma_pv128_commit_w(tO, tP, make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES)), idesc_pv, j > 0 ? 1u : 0u,
+                                            has_next ? &p_free[x] : &o_full[x]);
+                        if (!has_next) ++ocnt;
                     }
                     tc_commit_w(&v_empty[st]);
                 }
@@ -225,7 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
         const int x = (warp - 4) >> 2;          // which Q tile this warpgroup owns
         // turn-taking on the exp2 phase: warpgroup x syncs on barrier (2 + x) and hands over by arriving on (3 - x)
-        if (x == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 goes first
+        if (kTurns && x == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 goes first
         const int quad = warp & 3;              // TMEM lane quadrant
         const int r = quad * 32 + lane;         // row inside the Q tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -239,8 +236,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             if (qt >= a.n_qtiles) {
                 // phantom tile of the last pair: keep the turn-taking handshake in step with the other warpgroup
                 for (int j = 0; j < a.n_kv; ++j) {
-                    turn_wait(x);
-                    turn_pass(x);
+                    turn_wait<kTurns>(x);
+                    turn_pass<kTurns>(x);
                 }
                 continue;
             }
@@ -299,22 +296,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         tmem_st32(tO + 32, o1);
                     }
                 }
-                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-                turn_wait(x);                                                   // my turn on the MUFU pipe
+                // p = 2^(s log2e - m): packed FFMA2 for the argument, then kPoly of every 8 pairs take the FMA-pipe
+                // polynomial and the rest the MUFU (16 ex2/clk/SM is the binding unit at head dim 64); packed FADD2 sums.
+                uint64_t acc_a = 0, acc_b = 0;     // two independent packed accumulators (bit pattern of +0.0f, +0.0f)
+                const uint64_t l2e2 = f2_pack(kLog2e, kLog2e);
+                const uint64_t negm2 = f2_pack(-m_used, -m_used);
+                turn_wait<kTurns>(x);                                                   // my turn on the MUFU pipe
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(s[g][2 * c]), kLog2e, -m_used));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(s[g][2 * c + 1]), kLog2e, -m_used));
-                        if (c & 1) { acc2 += p0; acc3 += p1; } else { acc0 += p0; acc1 += p1; }
+                        const uint64_t arg = f2_fma(f2_pack(__uint_as_float(s[g][2 * c]), __uint_as_float(s[g][2 * c + 1])), l2e2, negm2);
+                        float a0, a1, p0, p1;
+                        f2_unpack(arg, a0, a1);
+                        uint64_t p2;
+                        if (kPoly == 9) {                       // timing experiment only: no exponential at all
+                            p2 = arg; p0 = a0; p1 = a1;
+                        } else if ((c & 7) < kPoly) {
+                            p2 = f2_exp2_poly(f2_pack(fmaxf(a0, -125.0f), fmaxf(a1, -125.0f)));
+                            f2_unpack(p2, p0, p1);
+                        } else {
+                            p0 = fast_exp2(a0);
+                            p1 = fast_exp2(a1);
+                            p2 = f2_pack(p0, p1);
+                        }
+                        if (c & 1) acc_b = f2_add(acc_b, p2); else acc_a = f2_add(acc_a, p2);
                         pk[c] = pack_bf16x2(p0, p1);
                     }
                     tmem_st16(tP + g * 16, pk);
                 }
-                turn_pass(x);                                                   // hand the MUFU pipe to the other tile
-                l_sum += (acc0 + acc1) + (acc2 + acc3);
+                turn_pass<kTurns>(x);                                                   // hand the MUFU pipe to the other tile
+                {
+                    float q0, q1;
+                    f2_unpack(f2_add(acc_a, acc_b), q0, q1);
+                    l_sum += q0 + q1;
+                }
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&p_full[x]);
@@ -355,7 +372,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         }
     }
     __syncwarp();
-    if (warp >= 4 && warp < 8) asm volatile("bar.sync 2, 256;" ::: "memory");   // absorb tile 1's final hand-over
+    if (kTurns && warp >= 4 && warp < 8) asm volatile("bar.sync 2, 256;" ::: "memory");   // absorb tile 1's final hand-over
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -378,14 +395,24 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
     a.n_kv = (L + ATT_BKV - 1) / ATT_BKV;
     a.total_work = B * NH * a.n_pairs;
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (check_cuda(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
-                       "cudaFuncSetAttribute(attention)"))
+    typedef void (*KernelFn)(const CUtensorMap, const AttArgs);
+    static KernelFn kern = nullptr;
+    if (kern == nullptr) {
+        // tuning switches (defaults are the measured best): MD_ATT_TURNS = MUFU turn-taking between the two softmax
+        // warpgroups, MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU
+        const char* e = getenv("MD_ATT_TURNS");
+        const int turns = e ? atoi(e) : 1;
+        e = getenv("MD_ATT_POLY");
+        const int poly = e ? atoi(e) : 3;
+        if (turns) kern = poly == 9 ? attention_kernel<true, 9> : poly == 8 ? attention_kernel<true, 8> : poly == 6 ? attention_kernel<true, 6> : poly == 5 ? attention_kernel<true, 5> : poly >= 4 ? attention_kernel<true, 4> : poly == 3 ? attention_kernel<true, 3> : poly == 2 ? attention_kernel<true, 2> : attention_kernel<true, 0>;
+        else kern = poly >= 4 ? attention_kernel<false, 4> : poly == 3 ? attention_kernel<false, 3> : poly == 2 ? attention_kernel<false, 2> : attention_kernel<false, 0>;
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
+                       "cudaFuncSetAttribute(attention)")) {
+            kern = nullptr;
             return MD_ERR_CUDA;
-        attr_set = true;
+        }
     }
     const int grid = a.total_work < num_sms() ? a.total_work : num_sms();
-    attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm, a);
+    kern<<<grid, kAttThreads, kAttSmem, stream>>>(tm, a);
     return check_cuda(cudaGetLastError(), "attention launch");
 }

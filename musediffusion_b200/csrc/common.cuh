@@ -251,6 +251,55 @@ MD_DEVINL void tma_load_3d_w(void* smem_dst, const CUtensorMap* m, uint64_t* bar
         : "memory");
 }
 
+// Batched forms: ONE election per group of MMAs + the commit that follows (the per-instruction ELECT / R2UR
+// sequence of the single forms costs more issue time than a 32-cycle N=64 MMA takes to execute).
+//   S[tmem_d] = Q K^T over 64 dims: four K=16 MMAs (SS), then commit -> bar
+MD_DEVINL void umma_qk64_commit_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q, pt, pf;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 pf, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pf;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(smem_u32(bar))
+        : "memory");
+}
+//   O[tmem_d] (+)= P[tmem_a] V over 128 keys: eight K=16 MMAs (TS; P advances 8 TMEM columns, V 2048 B per step),
+//   then commit -> bar
+MD_DEVINL void umma_pv128_commit_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                   uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q, pt, p0;\n\t.reg .b64 db;\n\t.reg .b32 ta;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+        "add.u32 ta, %1, 8;\n\tadd.u64 db, %2, 128;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 16;\n\tadd.u64 db, %2, 256;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 24;\n\tadd.u64 db, %2, 384;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 32;\n\tadd.u64 db, %2, 512;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 40;\n\tadd.u64 db, %2, 640;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 48;\n\tadd.u64 db, %2, 768;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 56;\n\tadd.u64 db, %2, 896;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor")
 // ----------------------------------------------------------------------------------------------
@@ -301,6 +350,44 @@ MD_DEVINL float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: two lanes per issue slot) ----
+MD_DEVINL uint64_t f2_pack(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+MD_DEVINL void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+MD_DEVINL uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+MD_DEVINL uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// 2^x for two lanes on the FMA pipe (no MUFU): Cody-Waite split x = n + f, n = rint(x) through the 1.5*2^23 magic
+// constant, 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (max rel. error 7.6e-5, far below bf16 rounding of
+// the result), exponent restored by adding n << 23 to the bit pattern.  Inputs must already be clamped to >= -125.
+MD_DEVINL uint64_t f2_exp2_poly(uint64_t x) {
+    const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
+    const uint64_t nmagic = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t neg1 = f2_pack(-1.0f, -1.0f);
+    const uint64_t r = f2_add(x, magic);                 // low mantissa bits = rint(x)
+    const uint64_t n = f2_add(r, nmagic);                // rint(x) as float
+    const uint64_t f = f2_fma(n, neg1, x);               // x - n in [-0.5, 0.5]
+    uint64_t p = f2_fma(f2_pack(0.05520550534129143f, 0.05520550534129143f), f, f2_pack(0.24261397123336792f, 0.24261397123336792f));
+    p = f2_fma(p, f, f2_pack(0.6932547688484192f, 0.6932547688484192f));
+    p = f2_fma(p, f, f2_pack(0.9999276995658875f, 0.9999276995658875f));
+    float p0, p1, r0, r1;
+    f2_unpack(p, p0, p1);
+    f2_unpack(r, r0, r1);
+    const uint32_t b0 = __float_as_uint(p0) + (__float_as_uint(r0) << 23);
+    const uint32_t b1 = __float_as_uint(p1) + (__float_as_uint(r1) << 23);
+    return f2_pack(__uint_as_float(b0), __uint_as_float(b1));
+}
+
 // erf-GELU (HF ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7).
 MD_DEVINL float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
