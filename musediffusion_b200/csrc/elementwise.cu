@@ -124,15 +124,18 @@ struct NoiseGen {
         }
         return c;
     }
+    template <bool kCentral>
     MD_DEVINL float one(uint32_t bits) const {
         const float q = fmaf((float)(bits >> 8), q_scale, q_bias);
-        return central ? norm_quantile_central(q) : norm_quantile(q + 0.5f);
+        return kCentral ? norm_quantile_central(q) : norm_quantile(q + 0.5f);
     }
     // four normals for the aligned group of 4 elements starting at global element index 4*g
-    MD_DEVINL float4 draw4(uint64_t g) const {
+    template <bool kCentral>
+    MD_DEVINL float4 draw4t(uint64_t g) const {
         const uint4 r = philox(make_uint4((uint32_t)g, (uint32_t)(g >> 32), step_lo, step_hi));
-        return make_float4(one(r.x), one(r.y), one(r.z), one(r.w));
+        return make_float4(one<kCentral>(r.x), one<kCentral>(r.y), one<kCentral>(r.z), one<kCentral>(r.w));
     }
+    MD_DEVINL float4 draw4(uint64_t g) const { return central ? draw4t<true>(g) : draw4t<false>(g); }
 };
 
 // flat float4 index -> (token, first element inside the token, sequence).  64-bit divisions cost ~100 instructions
@@ -202,75 +205,189 @@ struct StepArgs {
 
 MD_DEVINL float clampf(float v, int clip) { return clip ? fminf(fmaxf(v, -1.0f), 1.0f) : v; }
 
+// per-timestep scalars of one reverse step (computed once per thread when the whole batch shares t)
+struct StepCoef {
+    float c1, c2, sd;            // DDPM: mean = c1 pred + c2 x ; sample = mean + sd n
+    float sr, srm1, ca, cb, sn;  // DDIM
+};
 template <int MODE>
+MD_DEVINL StepCoef step_coef(const SchedRef& sched, int t, float eta) {
+    StepCoef k;
+    const float nz = (t != 0) ? 1.0f : 0.0f;
+    if (MODE == MD_STEP_DDPM) {
+        k.c1 = sched.get(TAB_C1, t);
+        k.c2 = sched.get(TAB_C2, t);
+        k.sd = __fmul_rn(nz, expf(__fmul_rn(0.5f, sched.get(TAB_LOGVAR, t))));
+    } else {
+        k.sr = sched.get(TAB_SR, t);
+        k.srm1 = sched.get(TAB_SRM1, t);
+        const float ab = sched.get(TAB_AB, t), abp = sched.get(TAB_ABP, t);
+        const float sigma = __fmul_rn(__fmul_rn(eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)))),
+                                      __fsqrt_rn(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+        k.ca = __fsqrt_rn(abp);
+        k.cb = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma)));
+        k.sn = __fmul_rn(nz, sigma);
+    }
+    return k;
+}
+// one element: same fp32 operation sequence as the reference's torch expressions (no FMA contraction)
+template <int MODE>
+MD_DEVINL float step_mean(const StepCoef& k, float x, float p) {
+    if (MODE == MD_STEP_DDPM) return __fadd_rn(__fmul_rn(k.c1, p), __fmul_rn(k.c2, x));
+    return __fadd_rn(__fmul_rn(p, k.ca), __fmul_rn(k.cb, __fdiv_rn(__fsub_rn(__fmul_rn(k.sr, x), p), k.srm1)));
+}
+template <int MODE>
+MD_DEVINL float step_noise_scale(const StepCoef& k) { return MODE == MD_STEP_DDPM ? k.sd : k.sn; }
+
+constexpr int kStepUnroll = 4;   // float4 items in flight per thread: all loads of a group are issued before any math
+
+// NOISE: 0 = external tensor, 1 = in-kernel Philox + central-band quantile (0 < top_p <= 1), 2 = Philox + general quantile.
+// IdxT: int32_t when every element offset fits 31 bits (the usual case; 64-bit address arithmetic costs issue slots).
+template <int MODE, int NOISE, typename IdxT>
 __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
     const int vec_per_tok = a.D >> 2;
-    const int64_t total = (int64_t)a.B * a.L * vec_per_tok;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const TokPos tp = tok_pos(i, vec_per_tok, a.vshift, a.L);
-        const int64_t tok = tp.tok;
-        const int d = tp.d;
-        const int t = a.t[tp.b * a.t_stride];
-        const int64_t off = tok * a.D + d;
-        const float4 x = ld_stream_f4(a.x_t + off);
-        float4 pr;
-        if (a.idx != nullptr) pr = *reinterpret_cast<const float4*>(a.E + (int64_t)a.idx[tok] * a.D + d);
-        else pr = ld_stream_f4(a.pred_in + off);
-        pr.x = clampf(pr.x, a.clip); pr.y = clampf(pr.y, a.clip); pr.z = clampf(pr.z, a.clip); pr.w = clampf(pr.w, a.clip);
-        if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off, pr);
-        float4 n;
-        if (a.noise != nullptr) n = ld_stream_f4(a.noise + off);
-        else n = a.rng.draw4((uint64_t)(((a.seq_offset * a.L) * a.D + off) >> 2));
-        const float nz = (t != 0) ? 1.0f : 0.0f;
-        float4 o;
-        if (MODE == MD_STEP_DDPM) {
-            // mean = c1 * pred + c2 * x ; sample = mean + (nz * exp(0.5 * logvar)) * noise   (no FMA contraction:
-            // same fp32 op sequence as the reference's torch expression)
-            const float c1 = a.sched.get(TAB_C1, t), c2 = a.sched.get(TAB_C2, t);
-            const float sd = __fmul_rn(nz, expf(__fmul_rn(0.5f, a.sched.get(TAB_LOGVAR, t))));
-            float4 mu;
-            mu.x = __fadd_rn(__fmul_rn(c1, pr.x), __fmul_rn(c2, x.x));
-            mu.y = __fadd_rn(__fmul_rn(c1, pr.y), __fmul_rn(c2, x.y));
-            mu.z = __fadd_rn(__fmul_rn(c1, pr.z), __fmul_rn(c2, x.z));
-            mu.w = __fadd_rn(__fmul_rn(c1, pr.w), __fmul_rn(c2, x.w));
-            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off, mu);
-            o.x = __fadd_rn(mu.x, __fmul_rn(sd, n.x));
-            o.y = __fadd_rn(mu.y, __fmul_rn(sd, n.y));
-            o.z = __fadd_rn(mu.z, __fmul_rn(sd, n.z));
-            o.w = __fadd_rn(mu.w, __fmul_rn(sd, n.w));
-        } else {
-            const float sr = a.sched.get(TAB_SR, t), srm1 = a.sched.get(TAB_SRM1, t);
-            const float ab = a.sched.get(TAB_AB, t), abp = a.sched.get(TAB_ABP, t);
-            const float sigma = __fmul_rn(__fmul_rn(a.eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)))),
-                                          __fsqrt_rn(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
-            const float ca = __fsqrt_rn(abp);
-            const float cb = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma)));
-            const float sn = __fmul_rn(nz, sigma);
-#define MD_DDIM_MEAN(X, P) __fadd_rn(__fmul_rn(P, ca), __fmul_rn(cb, __fdiv_rn(__fsub_rn(__fmul_rn(sr, X), P), srm1)))
-            float4 mu;
-            mu.x = MD_DDIM_MEAN(x.x, pr.x);
-            mu.y = MD_DDIM_MEAN(x.y, pr.y);
-            mu.z = MD_DDIM_MEAN(x.z, pr.z);
-            mu.w = MD_DDIM_MEAN(x.w, pr.w);
-#undef MD_DDIM_MEAN
-            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off, mu);
-            o.x = __fadd_rn(mu.x, __fmul_rn(sn, n.x));
-            o.y = __fadd_rn(mu.y, __fmul_rn(sn, n.y));
-            o.z = __fadd_rn(mu.z, __fmul_rn(sn, n.z));
-            o.w = __fadd_rn(mu.w, __fmul_rn(sn, n.w));
+    const IdxT total = (IdxT)((int64_t)a.B * a.L * vec_per_tok);
+    const IdxT nthreads = (IdxT)gridDim.x * (IdxT)blockDim.x;
+    const bool uniform_t = (a.t_stride == 0);
+    StepCoef ku;
+    if (uniform_t) ku = step_coef<MODE>(a.sched, a.t[0], a.eta);
+    for (IdxT i0 = (IdxT)blockIdx.x * (IdxT)blockDim.x + (IdxT)threadIdx.x; i0 < total; i0 += nthreads * kStepUnroll) {
+        IdxT off[kStepUnroll], tok[kStepUnroll];
+        int bq[kStepUnroll], dd[kStepUnroll];
+        bool ok[kStepUnroll];
+        float4 x[kStepUnroll], pr[kStepUnroll], n[kStepUnroll];
+        int32_t id[kStepUnroll], mk[kStepUnroll];
+        // ---- phase 1: addresses + independent loads
+#pragma unroll
+        for (int u = 0; u < kStepUnroll; ++u) {
+            const IdxT i = i0 + (IdxT)u * nthreads;
+            ok[u] = i < total;
+            const TokPos tp = tok_pos(ok[u] ? (int64_t)i : 0, vec_per_tok, a.vshift, a.L);
+            tok[u] = (IdxT)tp.tok; dd[u] = tp.d; bq[u] = tp.b;
+            off[u] = (IdxT)tp.tok * (IdxT)a.D + (IdxT)tp.d;
+            if (ok[u]) {
+                x[u] = ld_stream_f4(a.x_t + off[u]);
+                id[u] = (a.idx != nullptr) ? a.idx[tok[u]] : 0;
+                if (a.idx == nullptr) pr[u] = ld_stream_f4(a.pred_in + off[u]);
+                if (NOISE == 0) n[u] = ld_stream_f4(a.noise + off[u]);
+                mk[u] = (a.mask != nullptr && a.mask_d_stride == 0) ? a.mask[tok[u] * a.mask_tok_stride] : 1;
+            }
         }
-        if (a.mask != nullptr) {
-            const int32_t* mp = a.mask + tok * a.mask_tok_stride + (int64_t)d * a.mask_d_stride;
-            const float4 xs = *reinterpret_cast<const float4*>(a.x_start + off);
-            const int64_t ds = a.mask_d_stride;
-            if (mp[0] == 0) o.x = xs.x;
-            if (mp[ds] == 0) o.y = xs.y;
-            if (mp[2 * ds] == 0) o.z = xs.z;
-            if (mp[3 * ds] == 0) o.w = xs.w;
+        // ---- phase 2: dependent gather of the rounded embedding rows (E is L2-resident)
+        if (a.idx != nullptr) {
+#pragma unroll
+            for (int u = 0; u < kStepUnroll; ++u)
+                if (ok[u]) pr[u] = *reinterpret_cast<const float4*>(a.E + (int64_t)id[u] * a.D + dd[u]);
         }
-        st_stream_f4(a.x_out + off, o);
-        if (a.out_bf16 != nullptr)
-            *reinterpret_cast<uint2*>(a.out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        // ---- phase 3: arithmetic + stores
+#pragma unroll
+        for (int u = 0; u < kStepUnroll; ++u) {
+            if (!ok[u]) continue;
+            const StepCoef k = uniform_t ? ku : step_coef<MODE>(a.sched, a.t[bq[u] * a.t_stride], a.eta);
+            float4 p = pr[u];
+            p.x = clampf(p.x, a.clip); p.y = clampf(p.y, a.clip); p.z = clampf(p.z, a.clip); p.w = clampf(p.w, a.clip);
+            if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off[u], p);
+            const float4 nn = (NOISE == 0) ? n[u]
+                              : a.rng.template draw4t<NOISE == 1>((uint64_t)(((a.seq_offset * a.L) * a.D + (int64_t)off[u]) >> 2));
+            float4 mu;
+            mu.x = step_mean<MODE>(k, x[u].x, p.x);
+            mu.y = step_mean<MODE>(k, x[u].y, p.y);
+            mu.z = step_mean<MODE>(k, x[u].z, p.z);
+            mu.w = step_mean<MODE>(k, x[u].w, p.w);
+            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off[u], mu);
+            const float sc = step_noise_scale<MODE>(k);
+            float4 o;
+            o.x = __fadd_rn(mu.x, __fmul_rn(sc, nn.x));
+            o.y = __fadd_rn(mu.y, __fmul_rn(sc, nn.y));
+            o.z = __fadd_rn(mu.z, __fmul_rn(sc, nn.z));
+            o.w = __fadd_rn(mu.w, __fmul_rn(sc, nn.w));
+            if (a.mask != nullptr) {
+                if (a.mask_d_stride == 0) {
+                    // token-broadcast mask (what run/sample.py builds): x_start is touched only at kept positions
+                    if (mk[u] == 0) o = *reinterpret_cast<const float4*>(a.x_start + off[u]);
+                } else {
+                    const int32_t* mp = a.mask + tok[u] * a.mask_tok_stride + (int64_t)dd[u] * a.mask_d_stride;
+                    const int64_t ds = a.mask_d_stride;
+                    const bool k0 = mp[0] == 0, k1 = mp[ds] == 0, k2 = mp[2 * ds] == 0, k3 = mp[3 * ds] == 0;
+                    if (k0 | k1 | k2 | k3) {
+                        const float4 xs = *reinterpret_cast<const float4*>(a.x_start + off[u]);
+                        if (k0) o.x = xs.x;
+                        if (k1) o.y = xs.y;
+                        if (k2) o.z = xs.z;
+                        if (k3) o.w = xs.w;
+                    }
+                }
+            }
+            st_stream_f4(a.x_out + off[u], o);
+            if (a.out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(a.out_bf16 + off[u]) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+// Fast path for the shape the sampling loops actually use: D = 128 (one warp = one token row, lane = float4 column),
+// token-broadcast or absent mask, fewer than 2^24 tokens.  Four tokens per warp iteration, all loads first; addresses
+// are 32-bit and need no divisions (the per-sequence schedule index is only looked up when t is not shared).
+template <int MODE, int NOISE>
+__global__ void __launch_bounds__(256) posterior_step_d128_kernel(const StepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int M = a.B * a.L;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool uniform_t = (a.t_stride == 0);
+    StepCoef ku;
+    if (uniform_t) ku = step_coef<MODE>(a.sched, a.t[0], a.eta);
+    const uint64_t g_base = (uint64_t)(a.seq_offset * a.L) * 32u + (uint32_t)lane;     // float4 index of token 0, this lane
+    for (int tok0 = warp_global * kStepUnroll; tok0 < M; tok0 += nwarps * kStepUnroll) {
+        float4 x[kStepUnroll], pr[kStepUnroll], n[kStepUnroll];
+        int32_t id[kStepUnroll], mk[kStepUnroll];
+#pragma unroll
+        for (int u = 0; u < kStepUnroll; ++u) {
+            const int tok = tok0 + u;
+            if (tok < M) {
+                const uint32_t off = (uint32_t)tok * 128u + (uint32_t)lane * 4u;
+                x[u] = ld_stream_f4(a.x_t + off);
+                if (a.idx != nullptr) id[u] = a.idx[tok];
+                else pr[u] = ld_stream_f4(a.pred_in + off);
+                if (NOISE == 0) n[u] = ld_stream_f4(a.noise + off);
+                mk[u] = (a.mask != nullptr) ? a.mask[(int64_t)tok * a.mask_tok_stride] : 1;
+            }
+        }
+        if (a.idx != nullptr) {
+#pragma unroll
+            for (int u = 0; u < kStepUnroll; ++u)
+                if (tok0 + u < M) pr[u] = *reinterpret_cast<const float4*>(a.E + (uint32_t)id[u] * 128u + (uint32_t)lane * 4u);
+        }
+#pragma unroll
+        for (int u = 0; u < kStepUnroll; ++u) {
+            const int tok = tok0 + u;
+            if (tok >= M) break;
+            const uint32_t off = (uint32_t)tok * 128u + (uint32_t)lane * 4u;
+            const StepCoef k = uniform_t ? ku : step_coef<MODE>(a.sched, a.t[tok / a.L], a.eta);
+            float4 p = pr[u];
+            p.x = clampf(p.x, a.clip); p.y = clampf(p.y, a.clip); p.z = clampf(p.z, a.clip); p.w = clampf(p.w, a.clip);
+            if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off, p);
+            const float sc = step_noise_scale<MODE>(k);
+            // sigma == 0 (DDIM with eta = 0, or t == 0): the product sc * n is exactly 0 for any finite n -> skip the RNG
+            float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NOISE == 0) nn = n[u];
+            else if (sc != 0.0f) nn = a.rng.template draw4t<NOISE == 1>(g_base + (uint64_t)tok * 32u);
+            float4 mu;
+            mu.x = step_mean<MODE>(k, x[u].x, p.x);
+            mu.y = step_mean<MODE>(k, x[u].y, p.y);
+            mu.z = step_mean<MODE>(k, x[u].z, p.z);
+            mu.w = step_mean<MODE>(k, x[u].w, p.w);
+            if (a.mean_out != nullptr) st_stream_f4(a.mean_out + off, mu);
+            float4 o;
+            o.x = __fadd_rn(mu.x, __fmul_rn(sc, nn.x));
+            o.y = __fadd_rn(mu.y, __fmul_rn(sc, nn.y));
+            o.z = __fadd_rn(mu.z, __fmul_rn(sc, nn.z));
+            o.w = __fadd_rn(mu.w, __fmul_rn(sc, nn.w));
+            if (mk[u] == 0) o = *reinterpret_cast<const float4*>(a.x_start + off);     // kept (conditioning) position
+            st_stream_f4(a.x_out + off, o);
+            if (a.out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(a.out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
     }
 }
 
@@ -600,9 +717,32 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride; a.x_start = x_start; a.x_out = x_out;
     a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
     a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref(); a.vshift = vec_shift(D);
-    const int grid = ew_grid((int64_t)B * L * (D / 4), 256);
-    if (mode == MD_STEP_DDPM) posterior_step_kernel<MD_STEP_DDPM><<<grid, 256, 0, stream>>>(a);
-    else posterior_step_kernel<MD_STEP_DDIM><<<grid, 256, 0, stream>>>(a);
+    const int grid = ew_grid(((int64_t)B * L * (D / 4) + kStepUnroll - 1) / kStepUnroll, 256);
+    const int nz = (noise != nullptr) ? 0 : (a.rng.central ? 1 : 2);
+    if (D == 128 && (mask == nullptr || mask_d_stride == 0) && (int64_t)B * L < (1 << 24)) {
+        const int g2 = ew_grid(((int64_t)B * L + kStepUnroll - 1) / kStepUnroll * 32, 256);
+#define MD_LAUNCH_FAST(MODE_)                                                                                     \
+    do {                                                                                                          \
+        if (nz == 0) posterior_step_d128_kernel<MODE_, 0><<<g2, 256, 0, stream>>>(a);                             \
+        else if (nz == 1) posterior_step_d128_kernel<MODE_, 1><<<g2, 256, 0, stream>>>(a);                        \
+        else posterior_step_d128_kernel<MODE_, 2><<<g2, 256, 0, stream>>>(a);                                     \
+    } while (0)
+        if (mode == MD_STEP_DDPM) MD_LAUNCH_FAST(MD_STEP_DDPM); else MD_LAUNCH_FAST(MD_STEP_DDIM);
+#undef MD_LAUNCH_FAST
+        return check_cuda(cudaGetLastError(), "posterior_step launch");
+    }
+    const bool small = (int64_t)B * L * D + (int64_t)grid * 256 * kStepUnroll * 4 < ((int64_t)1 << 31);
+#define MD_LAUNCH_STEP(MODE_, NZ_)                                                                     \
+    do {                                                                                               \
+        if (small) posterior_step_kernel<MODE_, NZ_, int32_t><<<grid, 256, 0, stream>>>(a);            \
+        else posterior_step_kernel<MODE_, NZ_, int64_t><<<grid, 256, 0, stream>>>(a);                  \
+    } while (0)
+    if (mode == MD_STEP_DDPM) {
+        if (nz == 0) MD_LAUNCH_STEP(MD_STEP_DDPM, 0); else if (nz == 1) MD_LAUNCH_STEP(MD_STEP_DDPM, 1); else MD_LAUNCH_STEP(MD_STEP_DDPM, 2);
+    } else {
+        if (nz == 0) MD_LAUNCH_STEP(MD_STEP_DDIM, 0); else if (nz == 1) MD_LAUNCH_STEP(MD_STEP_DDIM, 1); else MD_LAUNCH_STEP(MD_STEP_DDIM, 2);
+    }
+#undef MD_LAUNCH_STEP
     return check_cuda(cudaGetLastError(), "posterior_step launch");
 }
 
