@@ -32,10 +32,14 @@ constexpr int ATT_BQ = 128;        // rows per Q tile
 constexpr int ATT_BKV = 128;       // keys per K/V stage
 constexpr int ATT_DH = 64;
 constexpr int ATT_STAGES = 3;
-constexpr int kAttThreads = 384;
-constexpr int kRegsProducer = 72, kRegsSoftmax = 216;   // 128*72 + 256*216 = 64512 = 384 threads x 168 regs at launch (the CTA pool)
+// kSplit = softmax warps per TMEM lane quadrant of a Q tile: 1 -> one thread owns a whole 128-key row of S,
+// 2 -> two threads own 64 keys each (twice the warps to hide the serial LDTM -> max -> exp -> STTM chain).
+template <int kSplit> struct AttCfg;
+template <> struct AttCfg<1> { static constexpr int kThreads = 384, kRegsProducer = 72, kRegsSoftmax = 216; };   // 128*72 + 256*216 = 64512 = 384 x 168
+template <> struct AttCfg<2> { static constexpr int kThreads = 640, kRegsProducer = 56, kRegsSoftmax = 104; };   // 128*56 + 512*104 = 60416 <= 640 x 96
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
-constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256;
+constexpr int kAttXchgBytes = (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;   // row-max (double buffered) and row-sum exchange between the two column halves
+constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256 + kAttXchgBytes;
 // TMEM columns (all 512 used): S and P have separate homes so that S(j+1) = Q K^T can be issued as soon as the softmax
 // warpgroup has READ S(j) into registers — the tensor pipe's latency leaves the softmax critical path.
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
@@ -49,7 +53,13 @@ struct AttArgs {
     int n_kv;           // ceil(L/128)
     int total_work;     // B * NH * n_pairs
     __nv_bfloat16* out; // [B*L, NH*64]
+    long long* trace;   // optional [role 4][event 8][step 64] clock64 stamps of CTA 0 (debug / tuning)
 };
+#define MD_TRACE(role, ev, step)                                                                          \
+    do {                                                                                                  \
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (step) < 64)                            \
+            a.trace[((role) * 8 + (ev)) * 64 + (step)] = clock64();                                       \
+    } while (0)
 
 struct Work { int b, h, pair; };
 MD_DEVINL Work decode_work(int w, const AttArgs& a) {
@@ -61,21 +71,21 @@ MD_DEVINL Work decode_work(int w, const AttArgs& a) {
     return r;
 }
 
-template <bool kTurns>
+template <bool kTurns, int kN>
 MD_DEVINL void turn_wait(int x) {
     if (!kTurns) return;
-    if (x == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
-    else asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (x == 0) asm volatile("bar.sync 2, %0;" ::"n"(kN) : "memory");
+    else asm volatile("bar.sync 3, %0;" ::"n"(kN) : "memory");
 }
-template <bool kTurns>
+template <bool kTurns, int kN>
 MD_DEVINL void turn_pass(int x) {
     if (!kTurns) return;
-    if (x == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-    else asm volatile("bar.arrive 2, 256;" ::: "memory");
+    if (x == 0) asm volatile("bar.arrive 3, %0;" ::"n"(kN) : "memory");
+    else asm volatile("bar.arrive 2, %0;" ::"n"(kN) : "memory");
 }
 
-template <bool kTurns, int kPoly>
-__global__ void __launch_bounds__(kAttThreads, 1)
+template <bool kTurns, int kPoly, int kSplit>
+__global__ void __launch_bounds__(AttCfg<kSplit>::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,6 +106,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     uint64_t* s_free = o_empty + 2;            // [2] softmax has read S into registers -> next Q K^T may overwrite it
     uint64_t* p_free = s_free + 2;             // [2] P V of the previous block retired -> P / O may be rewritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+    float* sMax = reinterpret_cast<float*>(bars) + 64;      // [tile][buf][half][128]   (barriers occupy < 256 B)
+    float* sSum = sMax + 2 * 2 * 2 * 128;                   // [tile][half][128]
+    constexpr int kTileThreads = 128 * kSplit;              // softmax threads per Q tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -113,10 +126,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
         }
         for (int x = 0; x < 2; ++x) {
             mbar_init(&s_full[x], 1);
-            mbar_init(&p_full[x], 128);
+            mbar_init(&p_full[x], kTileThreads);
             mbar_init(&o_full[x], 1);
-            mbar_init(&o_empty[x], 128);
-            mbar_init(&s_free[x], 128);
+            mbar_init(&o_empty[x], kTileThreads);
+            mbar_init(&s_free[x], kTileThreads);
             mbar_init(&p_free[x], 1);
         }
         fence_barrier_init();
@@ -128,7 +141,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AttCfg<kSplit>::kRegsProducer));
     if (warp == 0) {
         // =========================================================== TMA producer (whole warp, elected issue)
         {
@@ -196,6 +209,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                             mbar_wait(&s_free[x], (qcnt - 1) & 1);
                             ++qcnt;
                             tc_fence_after();
+                            MD_TRACE(x, 0, (int)(wcnt * a.n_kv + j));
                             umma_qk64_commit_w(tS, qd, make_sdesc_sw128(smem_u32(sK + st_n * ATT_TILE_BYTES)), idesc_qk, &s_full[x]);
                         }
                         tc_commit_w(&k_empty[st_n]);
@@ -203,9 +217,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     mbar_wait(&v_full[st], ph);
                     if (active) {
                         if (j == 0) mbar_wait(&o_empty[x], (ocnt & 1) ^ 1);   // previous item's O drained
+                        MD_TRACE(x, 1, (int)(wcnt * a.n_kv + j));
                         mbar_wait(&p_full[x], pcnt & 1);
                         ++pcnt;
                         tc_fence_after();
+                        MD_TRACE(x, 2, (int)(wcnt * a.n_kv + j));
                         umma_pv128_commit_w(tO, tP, make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES)), idesc_pv, j > 0 ? 1u : 0u,
                                             has_next ? &p_free[x] : &o_full[x]);
                         if (!has_next) ++ocnt;
@@ -219,42 +235,58 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     }
     } else {
         // =========================================================== softmax / correction / epilogue
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
-        const int x = (warp - 4) >> 2;          // which Q tile this warpgroup owns
-        // turn-taking on the exp2 phase: warpgroup x syncs on barrier (2 + x) and hands over by arriving on (3 - x)
-        if (kTurns && x == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 goes first
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AttCfg<kSplit>::kRegsSoftmax));
+        constexpr int NC = ATT_BKV / kSplit;     // keys (S columns) per thread
+        constexpr int NG = NC / 32;              // 32-column chunks per thread
+        constexpr int OC = ATT_DH / kSplit;      // O columns per thread
+        const int x = (warp - 4) / (4 * kSplit);            // which Q tile this warp works on
+        const int half = ((warp - 4) % (4 * kSplit)) >> 2;  // which column half (kSplit == 2)
+        // turn-taking on the exp2 phase: tile x syncs on barrier (2 + x) and hands over by arriving on (3 - x)
+        if (kTurns && x == 1) turn_pass<kTurns, 2 * kTileThreads>(1);   // tile 0 goes first
         const int quad = warp & 3;              // TMEM lane quadrant
         const int r = quad * 32 + lane;         // row inside the Q tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0) + lane_addr;
-        const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0) + lane_addr;
-        const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0) + lane_addr;
+        const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0) + lane_addr + half * NC;
+        const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0) + lane_addr + half * (NC / 2);
+        const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0) + lane_addr + half * OC;
         uint32_t scnt = 0, ocnt = 0, fcnt = 0;
         for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
             const Work wk = decode_work(w, a);
             const int qt = wk.pair * 2 + x;
             if (qt >= a.n_qtiles) {
-                // phantom tile of the last pair: keep the turn-taking handshake in step with the other warpgroup
+                // phantom tile of the last pair: keep the turn-taking handshake in step with the other tile
                 for (int j = 0; j < a.n_kv; ++j) {
-                    turn_wait<kTurns>(x);
-                    turn_pass<kTurns>(x);
+                    turn_wait<kTurns, 2 * kTileThreads>(x);
+                    turn_pass<kTurns, 2 * kTileThreads>(x);
                 }
                 continue;
             }
             float m_used = 0.f, l_sum = 0.f;
             for (int j = 0; j < a.n_kv; ++j, ++scnt) {
+                const bool tr = (half == 0 && quad == 0);
+                if (tr) MD_TRACE(2 + x, 0, (int)scnt);
                 mbar_wait(&s_full[x], scnt & 1);
                 tc_fence_after();
-                uint32_t s[4][32];
+                if (tr) MD_TRACE(2 + x, 1, (int)scnt);
+                if (kPoly == 10) {      // timing experiment only: barrier handshakes, no TMEM traffic, no math
+                    tc_fence_before();
+                    mbar_arrive(&s_free[x]);
+                    if (j > 0) { mbar_wait(&p_free[x], fcnt & 1); ++fcnt; tc_fence_after(); }
+                    tc_fence_before();
+                    mbar_arrive(&p_full[x]);
+                    continue;
+                }
+                uint32_t s[NG][32];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) tmem_ld32(tS + 32 * g, s[g]);
+                for (int g = 0; g < NG; ++g) tmem_ld32(tS + 32 * g, s[g]);
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&s_free[x]);               // S is in registers: the next Q K^T may overwrite it
-                const int valid = a.L - j * ATT_BKV;   // keys in this block that exist
-                if (valid < ATT_BKV) {
+                if (tr) MD_TRACE(2 + x, 2, (int)scnt);
+                const int valid = a.L - j * ATT_BKV - half * NC;   // keys of this thread's columns that exist
+                if (valid < NC) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
+                    for (int g = 0; g < NG; ++g)
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             if (g * 32 + c >= valid) s[g][c] = 0xff800000u;   // -inf
@@ -262,7 +294,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 float mx0 = __uint_as_float(s[0][0]), mx1 = __uint_as_float(s[0][1]), mx2 = __uint_as_float(s[0][2]),
                       mx3 = __uint_as_float(s[0][3]);
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
+                for (int g = 0; g < NG; ++g)
 #pragma unroll
                     for (int c = (g == 0 ? 4 : 0); c < 32; c += 4) {
                         mx0 = fmaxf(mx0, __uint_as_float(s[g][c]));
@@ -270,7 +302,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         mx2 = fmaxf(mx2, __uint_as_float(s[g][c + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(s[g][c + 3]));
                     }
-                const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;
+                float mrow = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (kSplit == 2) {
+                    // the two threads of a row exchange their partial maxima (double-buffered by block parity)
+                    float* mx = sMax + ((x * 2 + (j & 1)) * 2) * 128;
+                    mx[half * 128 + r] = mrow;
+                    if (x == 0) asm volatile("bar.sync 4, %0;" ::"n"(kTileThreads) : "memory");
+                    else asm volatile("bar.sync 5, %0;" ::"n"(kTileThreads) : "memory");
+                    mrow = fmaxf(mrow, mx[(half ^ 1) * 128 + r]);
+                }
+                if (tr) MD_TRACE(2 + x, 3, (int)scnt);
+                const float mb = mrow * kLog2e;        // -inf only if the whole block is masked for this row: impossible (block 0 ...)
                 if (j == 0) {
                     m_used = mb;
                 } else {
@@ -283,17 +325,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         const float f = need ? fast_exp2(m_used - mb) : 1.0f;
                         if (need) m_used = mb;
                         l_sum *= f;
-                        uint32_t o0[32], o1[32];
-                        tmem_ld32(tO, o0);
-                        tmem_ld32(tO + 32, o1);
-                        tc_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            o0[c] = __float_as_uint(__uint_as_float(o0[c]) * f);
-                            o1[c] = __float_as_uint(__uint_as_float(o1[c]) * f);
+                        for (int g = 0; g < OC / 32; ++g) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + 32 * g, o);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+                            tmem_st32(tO + 32 * g, o);
                         }
-                        tmem_st32(tO, o0);
-                        tmem_st32(tO + 32, o1);
                     }
                 }
                 // p = 2^(s log2e - m): packed FFMA2 for the argument, then kPoly of every 8 pairs take the FMA-pipe
@@ -301,9 +341,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 uint64_t acc_a = 0, acc_b = 0;     // two independent packed accumulators (bit pattern of +0.0f, +0.0f)
                 const uint64_t l2e2 = f2_pack(kLog2e, kLog2e);
                 const uint64_t negm2 = f2_pack(-m_used, -m_used);
-                turn_wait<kTurns>(x);                                                   // my turn on the MUFU pipe
+                if (tr) MD_TRACE(2 + x, 4, (int)scnt);
+                turn_wait<kTurns, 2 * kTileThreads>(x);                                 // my turn on the MUFU pipe
+                if (tr) MD_TRACE(2 + x, 5, (int)scnt);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < NG; ++g) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
@@ -326,7 +368,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     }
                     tmem_st16(tP + g * 16, pk);
                 }
-                turn_pass<kTurns>(x);                                                   // hand the MUFU pipe to the other tile
+                turn_pass<kTurns, 2 * kTileThreads>(x);                                 // hand the MUFU pipe to the other tile
+                if (tr) MD_TRACE(2 + x, 6, (int)scnt);
                 {
                     float q0, q1;
                     f2_unpack(f2_add(acc_a, acc_b), q0, q1);
@@ -335,44 +378,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&p_full[x]);
+                if (tr) MD_TRACE(2 + x, 7, (int)scnt);
             }
             // ---- epilogue: O / l -> bf16 -> global
+            if (kSplit == 2) {
+                float* sm = sSum + x * 2 * 128;
+                sm[half * 128 + r] = l_sum;
+                if (x == 0) asm volatile("bar.sync 4, %0;" ::"n"(kTileThreads) : "memory");
+                else asm volatile("bar.sync 5, %0;" ::"n"(kTileThreads) : "memory");
+                l_sum += sm[(half ^ 1) * 128 + r];
+            }
             mbar_wait(&o_full[x], ocnt & 1);
             ++ocnt;
             tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tO, o0);
-            tmem_ld32(tO + 32, o1);
+            uint32_t o[OC / 32][32];
+#pragma unroll
+            for (int g = 0; g < OC / 32; ++g) tmem_ld32(tO + 32 * g, o[g]);
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(&o_empty[x]);
             const int row = qt * ATT_BQ + r;
             if (row < a.L) {
                 const float inv = 1.0f / l_sum;
-                __nv_bfloat16* dst = a.out + ((size_t)wk.b * a.L + row) * H + wk.h * ATT_DH;
+                __nv_bfloat16* dst = a.out + ((size_t)wk.b * a.L + row) * H + wk.h * ATT_DH + half * OC;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
-                    u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
-                    u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
-                    u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + g * 8) = u;
-                }
+                for (int gg = 0; gg < OC / 32; ++gg)
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
-                    u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
-                    u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
-                    u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
-                }
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 0]) * inv, __uint_as_float(o[gg][g * 8 + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 2]) * inv, __uint_as_float(o[gg][g * 8 + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 4]) * inv, __uint_as_float(o[gg][g * 8 + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 6]) * inv, __uint_as_float(o[gg][g * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + gg * 32 + g * 8) = u;
+                    }
             }
         }
     }
     __syncwarp();
-    if (kTurns && warp >= 4 && warp < 8) asm volatile("bar.sync 2, 256;" ::: "memory");   // absorb tile 1's final hand-over
+    if (kTurns && warp >= 4 && warp < 4 + 4 * kSplit) turn_wait<kTurns, 2 * kTileThreads>(0);   // absorb tile 1's final hand-over
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -395,17 +439,28 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
     a.n_kv = (L + ATT_BKV - 1) / ATT_BKV;
     a.total_work = B * NH * a.n_pairs;
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a.trace = nullptr;
+    if (const char* tp = getenv("MD_ATT_TRACE_PTR")) a.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
     typedef void (*KernelFn)(const CUtensorMap, const AttArgs);
     static KernelFn kern = nullptr;
+    static int threads = 0;
     if (kern == nullptr) {
-        // tuning switches (defaults are the measured best): MD_ATT_TURNS = MUFU turn-taking between the two softmax
-        // warpgroups, MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU
+        // tuning switches (defaults are the measured best): MD_ATT_TURNS = MUFU turn-taking between the two Q tiles,
+        // MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU,
+        // MD_ATT_SPLIT = softmax threads per S row (1 or 2)
         const char* e = getenv("MD_ATT_TURNS");
         const int turns = e ? atoi(e) : 1;
         e = getenv("MD_ATT_POLY");
         const int poly = e ? atoi(e) : 3;
-        if (turns) kern = poly == 9 ? attention_kernel<true, 9> : poly == 8 ? attention_kernel<true, 8> : poly == 6 ? attention_kernel<true, 6> : poly == 5 ? attention_kernel<true, 5> : poly >= 4 ? attention_kernel<true, 4> : poly == 3 ? attention_kernel<true, 3> : poly == 2 ? attention_kernel<true, 2> : attention_kernel<true, 0>;
-        else kern = poly >= 4 ? attention_kernel<false, 4> : poly == 3 ? attention_kernel<false, 3> : poly == 2 ? attention_kernel<false, 2> : attention_kernel<false, 0>;
+        e = getenv("MD_ATT_SPLIT");
+        const int split = e ? atoi(e) : 1;
+#define MD_ATT_PICK(T_, S_)                                                                                               \
+    (poly == 10 ? attention_kernel<T_, 10, S_> : poly == 9 ? attention_kernel<T_, 9, S_> : poly >= 4 ? attention_kernel<T_, 4, S_> : poly == 3 ? attention_kernel<T_, 3, S_> \
+     : poly == 2 ? attention_kernel<T_, 2, S_> : attention_kernel<T_, 0, S_>)
+        if (split == 2) kern = turns ? MD_ATT_PICK(true, 2) : MD_ATT_PICK(false, 2);
+        else kern = turns ? MD_ATT_PICK(true, 1) : MD_ATT_PICK(false, 1);
+#undef MD_ATT_PICK
+        threads = split == 2 ? AttCfg<2>::kThreads : AttCfg<1>::kThreads;
         if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
                        "cudaFuncSetAttribute(attention)")) {
             kern = nullptr;
@@ -413,6 +468,6 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
         }
     }
     const int grid = a.total_work < num_sms() ? a.total_work : num_sms();
-    kern<<<grid, kAttThreads, kAttSmem, stream>>>(tm, a);
+    kern<<<grid, threads, kAttSmem, stream>>>(tm, a);
     return check_cuda(cudaGetLastError(), "attention launch");
 }
