@@ -215,7 +215,7 @@ def run_ours(args):
         top = max((v for v in breakdown.values() if v["flops"] > 0), key=lambda v: v["ms"])
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
         roofline = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": ncu_traffic(top["name"], B),
                     "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
                     "launches_per_step": top["launches"], "ms_per_step": top["ms"]}
     step_tflops = flops_per_sequence_step() * B / (ms_step * 1e-3) / 1e12
@@ -259,6 +259,18 @@ def run_ours(args):
                 "cpu_baseline": cpu_baseline, "kernels": breakdown}
         print(json.dumps(line))
     dist.barrier()
+
+
+def ncu_traffic(kernel, B):
+    """dram bytes (read + write) per launch from the committed `ncu --set full` capture (profiles/r1_traffic.json holds
+    bytes per sequence measured at 64 sequences); null when no capture exists for this kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        key = kernel.split(":")[0]
+        return float(t[key]["dram_bytes_per_sequence"]) * B if key in t else None
+    except Exception:
+        return None
 
 
 def summarize_profile(prof, B):

@@ -87,6 +87,19 @@ int md_round_argmin(const float* x, const float* E, int32_t* idx, float* margin,
 int md_logits_argmax(const float* x, const float* E, const float* bias, int32_t* tok, float* margin, int64_t M, int V,
                      int D, cudaStream_t stream);
 
+/* Tensor-core versions of the two reductions above (tcgen05, split-bf16 operands x = xh + xl, E = Eh + El with the four
+ * partial products accumulated in fp32: fp32-grade scores, the score matrix stays in TMEM).
+ *   md_embed_split: once per embedding matrix.  E2 = bf16 [Vp, 2D] = [Eh | El], sqnorm = fp32 [Vp] = |E_v|^2 (+inf on
+ *     the Vp - V padding rows), Vp = md_round_tc_padded_vocab(V).
+ *   md_round_argmin_tc: mode 0: idx[m] = argmin_v (cst[v] - 2 x_m.E_v), cst = sqnorm  (rounding.py:21-28; |x_m|^2 is
+ *     constant per row, the reference's clamp(dist, 0) only creates ties on bit-exact hits);
+ *     mode 1: idx[m] = argmax_v (x_m.E_v + cst[v]), cst = lm_head bias padded with -inf  (network.py:91-93 + argmax).
+ *     x2_ws: bf16 [M, 2D] scratch.  Lowest index wins ties.  D must be a multiple of 64. */
+int md_round_tc_padded_vocab(int V);
+int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, cudaStream_t stream);
+int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x2_ws, int32_t* idx, float* margin,
+                       int64_t M, int V, int D, int mode, cudaStream_t stream);
+
 /* ---- the fused per-step posterior update ----
  * x_{t-1} from x_t for mode DDPM (p_sample :349-404 with p_mean_variance :311-347, q_posterior_mean :257-278) or
  * DDIM (ddim_sample :701-757, _predict_eps_from_xstart :201-205):

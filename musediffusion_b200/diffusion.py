@@ -208,7 +208,12 @@ class GaussianDiffusion:
         E = rounding_weight_of(denoised_fn)
         idx = pred = None
         if E is not None:
-            idx = ops.round_argmin(model_output, E)                   # fused distance + argmin (rounding.py:21-28)
+            # fused distance contraction + row argmin (rounding.py:21-28); tcgen05 split-bf16 kernel when the embedding
+            # width allows it, fp32 CUDA-core kernel otherwise
+            if E.shape[1] % 64 == 0:
+                idx = ops.round_argmin_tc(model_output, ops.split_embedding(E))
+            else:
+                idx = ops.round_argmin(model_output, E)
         elif denoised_fn is not None:
             pred = denoised_fn(model_output, t if t.numel() == B else t.expand(B))   # arbitrary user callable
         else:

@@ -170,6 +170,58 @@ def logits_argmax(x, E, bias, want_margin=False):
     return (tok, margin) if want_margin else tok
 
 
+class SplitEmbedding:
+    """bf16 [Vp, 2D] = [Eh | El] split of an embedding matrix + |E_v|^2, built once per matrix version
+    (md_embed_split); `logit_cst(bias)` gives the padded per-column constants of the argmax-logits mode."""
+
+    def __init__(self, E):
+        E = _c(E.detach(), torch.float32)
+        self.V, self.D = E.shape
+        self.Vp = _lib.lib.md_round_tc_padded_vocab(self.V)
+        self.E2 = torch.empty((self.Vp, 2 * self.D), dtype=BF16, device=E.device)
+        self.sqnorm = torch.empty((self.Vp,), dtype=torch.float32, device=E.device)
+        call("md_embed_split", _p(E), self.V, self.D, _p(self.E2), _p(self.sqnorm), _stream())
+        self._ws = {}
+
+    def logit_cst(self, bias):
+        c = torch.full((self.Vp,), float("-inf"), dtype=torch.float32, device=self.E2.device)
+        c[:self.V] = bias.detach().float()
+        return c
+
+    def workspace(self, M):
+        ws = self._ws.get(M)
+        if ws is None:
+            self._ws = {M: torch.empty((M, 2 * self.D), dtype=BF16, device=self.E2.device)}
+            ws = self._ws[M]
+        return ws
+
+
+_split_cache = {}
+
+
+def split_embedding(E):
+    """cached SplitEmbedding for a weight tensor (keyed by storage + version, a handful of entries at most)."""
+    key = (E.data_ptr(), E._version, tuple(E.shape), str(E.device))
+    se = _split_cache.get(key)
+    if se is None:
+        if len(_split_cache) > 8:
+            _split_cache.clear()
+        se = SplitEmbedding(E)
+        _split_cache[key] = se
+    return se
+
+
+def round_argmin_tc(x, se, cst=None, mode=0, want_margin=False, out=None):
+    """tensor-core nearest-embedding ids (mode 0, cst = |E|^2) or argmax-logit ids (mode 1, cst = padded bias)."""
+    x = _c(x, torch.float32)
+    M = x.numel() // se.D
+    idx = out if out is not None else torch.empty((M,), dtype=torch.int32, device=x.device)
+    margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
+    call("md_round_argmin_tc", _p(x), _p(se.E2), _p(se.sqnorm if cst is None else cst), _p(se.workspace(M)), _p(idx),
+         _p(margin), M, se.V, se.D, mode, _stream())
+    return (idx, margin) if want_margin else idx
+
+
 # ------------------------------------------------------------------------------------------------ posterior step
 def _mask_args(mask, B, L, D):
     """mask: None, or an int tensor broadcastable to [B, L, D] (the reference passes a stride-0 expand of [B, L, 1])."""

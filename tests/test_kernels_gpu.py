@@ -185,6 +185,34 @@ def test_rounding_and_logits_random(M):
     assert ops.round_argmin(torch.zeros((0, 128), device=DEV), torch.from_numpy(E).to(DEV)).numel() == 0
 
 
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 5000, 70000])
+def test_rounding_tensor_core(M, golden_dir):
+    """tcgen05 split-bf16 rounding / decode: same ids as the fp32 oracle wherever the top-2 margin exceeds 1e-3."""
+    rng = np.random.default_rng(M + 1)
+    E = rng.standard_normal((729, 128)).astype(np.float32)
+    E[700] = E[5]
+    bias = rng.standard_normal(729).astype(np.float32)
+    x = (rng.standard_normal((M, 128)) * 0.8).astype(np.float32)
+    x[0] = E[700]                                      # exact hit on a duplicated row -> lowest index
+    se = ops.SplitEmbedding(torch.from_numpy(E).to(DEV))
+    idx, mg = ops.round_argmin_tc(torch.from_numpy(x).to(DEV), se, want_margin=True)
+    idx = idx.cpu().numpy()
+    ref_idx, dist = O.efficient_knn(E, x)
+    ref_margin = O.top2_margin(dist)
+    assert idx[0] == 5
+    bad = idx != ref_idx
+    assert not (bad & (ref_margin > 1e-3)).any(), (int(bad.sum()), float(ref_margin[bad].max()))
+    np.testing.assert_allclose(mg.cpu().numpy()[~bad], ref_margin[~bad], atol=3e-3)
+    tok = ops.round_argmin_tc(torch.from_numpy(x).to(DEV), se, cst=se.logit_cst(torch.from_numpy(bias).to(DEV)), mode=1).cpu().numpy()
+    logits = x.astype(np.float64) @ E.T.astype(np.float64) + bias
+    srt = np.sort(logits, axis=1)
+    bad = tok != logits.argmax(1)
+    assert not (bad & ((srt[:, -1] - srt[:, -2]) > 1e-3)).any()
+    g = np.load(__import__("os").path.join(golden_dir, "rounding.npz"))
+    seg = ops.SplitEmbedding(torch.from_numpy(g["E"]).to(DEV))
+    assert np.array_equal(ops.round_argmin_tc(torch.from_numpy(g["x"]).to(DEV), seg).cpu().numpy(), g["idx"])
+
+
 # ------------------------------------------------------------------------------------------------ posterior step
 def _schedule(T=2000):
     s = O.make_schedule("sqrt", T)

@@ -52,3 +52,6 @@ ms = timeit(lambda: ops.layernorm(h, g, bt, 1e-12, resid=r, out=ho))
 rep("layernorm(x + resid) bf16", ms, M * H * 2 * 3)
 ms = timeit(lambda: ops.round_argmin(x, E))
 print("%-42s %8.3f ms  %.1f TFLOP/s fp32" % ("round_argmin", ms, 2.0 * M * V * D / ms / 1e9))
+se = ops.SplitEmbedding(E)
+ms = timeit(lambda: ops.round_argmin_tc(x, se))
+print("%-42s %8.3f ms  %.1f TFLOP/s (4 x 2MVD split-bf16)  %.1f%% of HBM peak on %d algorithmic bytes/token" % ("round_argmin_tc", ms, 8.0 * M * 768 * D / ms / 1e9, 100 * M * 516 / ms / 1e6 / peak, 516))
