@@ -57,7 +57,7 @@ struct AttArgs {
 };
 #define MD_TRACE(role, ev, step)                                                                          \
     do {                                                                                                  \
-        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (step) < 64)                            \
+        if (kTrace && a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (step) < 64)                  \
             a.trace[((role) * 8 + (ev)) * 64 + (step)] = clock64();                                       \
     } while (0)
 
@@ -84,7 +84,7 @@ MD_DEVINL void turn_pass(int x) {
     else asm volatile("bar.arrive 2, %0;" ::"n"(kN) : "memory");
 }
 
-template <bool kTurns, int kPoly, int kSplit>
+template <bool kTurns, int kPoly, int kSplit, bool kTrace = false>
 __global__ void __launch_bounds__(AttCfg<kSplit>::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -460,6 +460,10 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
         if (split == 2) kern = turns ? MD_ATT_PICK(true, 2) : MD_ATT_PICK(false, 2);
         else kern = turns ? MD_ATT_PICK(true, 1) : MD_ATT_PICK(false, 1);
 #undef MD_ATT_PICK
+        if (getenv("MD_ATT_TRACE_PTR")) {      // timeline tracing build of the selected split (tools/att_trace.py)
+            if (split == 2) kern = turns ? attention_kernel<true, 0, 2, true> : attention_kernel<false, 0, 2, true>;
+            else kern = turns ? attention_kernel<true, 3, 1, true> : attention_kernel<false, 3, 1, true>;
+        }
         threads = split == 2 ? AttCfg<2>::kThreads : AttCfg<1>::kThreads;
         if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
                        "cudaFuncSetAttribute(attention)")) {
