@@ -13,5 +13,6 @@ if [ "${NCU_LIST:-0}" == "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-breakdown > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 fi
 for k in ${NCU_FULL}; do
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_$k python tools/profile_step.py --batch 64 --steps 2 > gpurun_out/ncu_$k.log 2>&1; echo "ncu full $k rc=$?"
+  kk=$(echo $k | tr -c "A-Za-z0-9_\n" "_")
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_$kk python tools/profile_step.py --batch 64 --steps 2 > gpurun_out/ncu_$kk.log 2>&1; echo "ncu full $k rc=$?"
 done
