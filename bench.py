@@ -29,6 +29,18 @@ DIFFUSION_STEPS = 2000
 L, D, V, H, F, NL, NH = 2096, 128, 729, 768, 3072, 12, 12
 
 
+def set_model_shape(args):
+    """--scaled switches to BASELINE.json config 5 (bert-large-shaped denoiser, 2x seq_len); individual flags override."""
+    global L, H, F, NL, NH
+    if args.scaled:
+        L, H, F, NL, NH = 4192, 1024, 4096, 24, 16
+    L = args.seq_len or L
+    H = args.hidden or H
+    F = args.ffn or F
+    NL = args.layers or NL
+    NH = args.heads or NH
+
+
 def flops_per_sequence_step():
     """L * [2(2DH + 2H^2) + NL(8H^2 + 4HF + 4LH) + 2VD]."""
     return L * (2 * (2 * D * H + 2 * H * H) + NL * (8 * H * H + 4 * H * F + 4 * L * H) + 2 * V * D)
@@ -123,8 +135,12 @@ def run_reference(args):
 
 
 def workload_config(batch_per_gpu, n_gpus, note=None):
-    c = {"workload": "BASELINE.json configs[1]: base TransformerNetModel (bert-base encoder 12x768, seq_len 2096, "
-                     "hidden_dim 128, vocab 729) random-init; modification (seq2seq) sampling, DDPM 2000 steps, "
+    base = (L, H, F, NL, NH) == (2096, 768, 3072, 12, 12)
+    c = {"workload": ("BASELINE.json configs[1]: base TransformerNetModel (bert-base encoder 12x768, seq_len 2096, "
+                      "hidden_dim 128, vocab 729)" if base else
+                      "BASELINE.json configs[4] family: scaled denoiser (encoder %dx%d, %d heads, FFN %d, seq_len %d, "
+                      "hidden_dim 128, vocab 729)" % (NL, H, NH, F, L)) +
+                     " random-init; modification (seq2seq) sampling, DDPM 2000 steps, "
                      "rounding every step, top_p=1; batch %d sequences per GPU" % batch_per_gpu,
          "global_batch": batch_per_gpu * n_gpus, "seq_len": L, "chain_steps": DIFFUSION_STEPS,
          "parallelism": "dp%d (batch sharded by sequence, replicated weights, no collective in the loop)" % n_gpus,
@@ -151,7 +167,9 @@ def run_ours(args):
     B = args.batch
     targs = SimpleNamespace(hidden_dim=D, hidden_t_dim=128, vocab_size=V, seq_len=L, dropout=0.1, noise_schedule="sqrt",
                             diffusion_steps=DIFFUSION_STEPS, timestep_respacing="", rescale_timesteps=True,
-                            predict_xstart=True)
+                            predict_xstart=True,
+                            encoder_config=dict(hidden_size=H, num_hidden_layers=NL, num_attention_heads=NH,
+                                                intermediate_size=F))
     torch.manual_seed(0)
     model, diffusion = create_model_and_diffusion(targs)
     model.eval().requires_grad_(False).to(dev)
@@ -328,7 +346,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaled", action="store_true", help="BASELINE.json config 5: hidden 1024, 24 layers, 16 heads, FFN 4096, seq_len 4192")
+    ap.add_argument("--seq-len", type=int, default=0)
+    ap.add_argument("--hidden", type=int, default=0)
+    ap.add_argument("--ffn", type=int, default=0)
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--heads", type=int, default=0)
     args = ap.parse_args()
+    set_model_shape(args)
+    if (L, H, F, NL, NH) != (2096, 768, 3072, 12, 12):
+        args.no_cpu_baseline = True      # the CPU port sample is sized for the base config only
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
