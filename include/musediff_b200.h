@@ -95,6 +95,9 @@ int md_logits_argmax(const float* x, const float* E, const float* bias, int32_t*
  *     constant per row, the reference's clamp(dist, 0) only creates ties on bit-exact hits);
  *     mode 1: idx[m] = argmax_v (x_m.E_v + cst[v]), cst = lm_head bias padded with -inf  (network.py:91-93 + argmax).
  *     x2_ws: bf16 [M, 2D] scratch.  Lowest index wins ties.  D must be a multiple of 64. */
+/* fp32 [rows, D] -> bf16 [rows, copies * 2D]: `copies` repetitions of the two-term split [hi | lo], hi = bf16(x),
+ * lo = bf16(x - hi)  (operand of the split-bf16 contractions: rounding, decode, get_logits). */
+int md_split_bf16(const float* x, void* out_bf16, int64_t rows, int D, int copies, cudaStream_t stream);
 int md_round_tc_padded_vocab(int V);
 int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, cudaStream_t stream);
 int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x2_ws, int32_t* idx, float* margin,

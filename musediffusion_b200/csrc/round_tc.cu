@@ -40,9 +40,9 @@ struct RoundTcArgs {
     float* margin;         // optional [M]
 };
 
-// fp32 [n] -> bf16 [n_rows, 2D] = [hi | lo] split, one float4 per thread
+// fp32 [rows, D] -> bf16 [rows, copies * 2D] = copies x [hi | lo] split, one float4 per thread
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows,
-                                                         int D) {
+                                                         int D, int copies) {
     const int vec = D >> 2;
     const int64_t total = rows * vec;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,9 +53,11 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
         const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
         const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
         const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-        __nv_bfloat16* o = out + r * 2 * D + c;
-        *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-        *reinterpret_cast<uint2*>(o + D) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        for (int k = 0; k < copies; ++k) {
+            __nv_bfloat16* o = out + (r * copies + k) * 2 * D + c;
+            *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(o + D) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
     }
 }
 
@@ -248,6 +250,13 @@ extern "C" __attribute__((visibility("default"))) int md_embed_split(const float
     return check_cuda(cudaGetLastError(), "embed_split launch");
 }
 
+extern "C" __attribute__((visibility("default"))) int md_split_bf16(const float* x, void* out, int64_t rows, int D, int copies, cudaStream_t stream) {
+    if (D <= 0 || D % 4 != 0 || copies < 1) { set_last_error("md_split_bf16: D=%d must be a positive multiple of 4, copies >= 1", D); return MD_ERR_ARG; }
+    if (rows == 0) return MD_OK;
+    split_bf16_kernel<<<ew_grid2(rows * (D / 4)), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), rows, D, copies);
+    return check_cuda(cudaGetLastError(), "split_bf16 launch");
+}
+
 extern "C" __attribute__((visibility("default"))) int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x2_ws, int32_t* idx, float* margin,
                                   int64_t M, int V, int D, int mode, cudaStream_t stream) {
     if (D % RT_BK != 0 || D <= 0) { set_last_error("md_round_argmin_tc: D=%d must be a positive multiple of %d", D, RT_BK); return MD_ERR_ARG; }
@@ -255,7 +264,7 @@ extern "C" __attribute__((visibility("default"))) int md_round_argmin_tc(const f
     if (mode != 0 && mode != 1) { set_last_error("md_round_argmin_tc: mode must be 0 (argmin distance) or 1 (argmax logit)"); return MD_ERR_ARG; }
     if (M == 0) return MD_OK;
     const int Vp = md_round_tc_padded_vocab(V);
-    split_bf16_kernel<<<ew_grid2(M * (D / 4)), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(x2_ws), M, D);
+    split_bf16_kernel<<<ew_grid2(M * (D / 4)), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(x2_ws), M, D, 1);
     if (int e = check_cuda(cudaGetLastError(), "split_bf16 launch")) return e;
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d(&tmA, x2_ws, 0, (uint64_t)M, 2 * D, 2 * D, RT_BM, RT_BK)) return e;

@@ -104,14 +104,16 @@ class WeightPack:
                 wo=bf(ao.dense.weight), bo=f32(ao.dense.bias), g1=f32(ao.LayerNorm.weight), b1=f32(ao.LayerNorm.bias),
                 w1=bf(lyr.intermediate.dense.weight), bi=f32(lyr.intermediate.dense.bias),
                 w2=bf(ff.dense.weight), b2=f32(ff.dense.bias), g2=f32(ff.LayerNorm.weight), b2n=f32(ff.LayerNorm.bias)))
-        # split-bf16 operands for near-fp32 logits on the tensor cores: x.E^T ~ xh.Eh + xh.El + xl.Eh  (K = 3 D)
+        # split-bf16 operands for fp32-grade logits on the tensor cores (get_logits):
+        #   x.E^T = [xh|xl|xh|xl] . [Eh|Eh|El|El]^T   (all four partial products, K = 4 D, fp32 accumulation)
         V, D = self.E.shape
         Vp = (V + 7) // 8 * 8
-        Ep = torch.zeros((Vp, D), dtype=torch.float32, device=dev)
-        Ep[:V] = self.E
-        Eh = Ep.to(torch.bfloat16)
-        El = (Ep - Eh.float()).to(torch.bfloat16)
-        self.E_split = torch.cat([Eh, El, Eh], dim=1).contiguous()
+        e2 = ops.split_bf16(self.E, copies=1)                       # [V, 2D] = [Eh | El]
+        self.E_split = torch.zeros((Vp, 4 * D), dtype=torch.bfloat16, device=dev)
+        self.E_split[:V, 0 * D:1 * D] = e2[:, :D]
+        self.E_split[:V, 1 * D:2 * D] = e2[:, :D]
+        self.E_split[:V, 2 * D:3 * D] = e2[:, D:]
+        self.E_split[:V, 3 * D:4 * D] = e2[:, D:]
         self.lm_bias_pad = torch.zeros((Vp,), dtype=torch.float32, device=dev)
         self.lm_bias_pad[:V] = self.lm_bias
         self.split = None          # SplitEmbedding for the tensor-core decode, built on first use
@@ -203,15 +205,12 @@ class TransformerNetModel(nn.Module):
 
     def get_logits(self, hidden_repr):
         """network.py:91-93 (logits_mode 1): lm_head(x) = x E^T + b as ONE tcgen05 GEMM over split-bf16 operands
-        (xh.Eh + xh.El + xl.Eh with fp32 accumulation: ~2^-16 relative, i.e. fp32-grade logits)."""
+        (all four partial products of x = xh + xl, E = Eh + El with fp32 accumulation: fp32-grade logits)."""
         if self.logits_mode != 1:
             raise NotImplementedError("logits_mode 2 is not used by the sampling path (run/sample.py:219)")
         pk = self.weight_pack()
         V, D = pk.E.shape
-        x = hidden_repr.reshape(-1, D).float()
-        xh = x.to(torch.bfloat16)
-        xl = (x - xh.float()).to(torch.bfloat16)
-        A = torch.cat([xh, xh, xl], dim=1).contiguous()
+        A = ops.split_bf16(hidden_repr.reshape(-1, D), copies=2)     # [M, 4D] = [xh|xl|xh|xl]
         out = ops.linear(A, pk.E_split, pk.lm_bias_pad, _lib.EPI_BIAS, out_dtype=torch.float32)
         return out[:, :V].reshape(*hidden_repr.shape[:-1], V).to(hidden_repr.dtype)
 

@@ -170,6 +170,16 @@ def logits_argmax(x, E, bias, want_margin=False):
     return (tok, margin) if want_margin else tok
 
 
+def split_bf16(x, copies=1):
+    """fp32 [..., D] -> bf16 [rows, copies * 2D] = copies x [hi | lo]."""
+    x = _c(x, torch.float32)
+    D = x.shape[-1]
+    rows = x.numel() // D
+    out = torch.empty((rows, copies * 2 * D), dtype=BF16, device=x.device)
+    call("md_split_bf16", _p(x), _p(out), rows, D, copies, _stream())
+    return out
+
+
 class SplitEmbedding:
     """bf16 [Vp, 2D] = [Eh | El] split of an embedding matrix + |E_v|^2, built once per matrix version
     (md_embed_split); `logit_cst(bias)` gives the padded per-column constants of the argmax-logits mode."""
