@@ -251,6 +251,71 @@ MD_DEVINL void tma_load_3d_w(void* smem_dst, const CUtensorMap* m, uint64_t* bar
         : "memory");
 }
 
+// ---- 2-CTA (cta_group::2) forms: one CTA pair = one 256-row MMA; the leader CTA issues, operands are read from both
+// CTAs' shared memory (each holds its own 128 A rows and half of the B rows), commits are multicast to both CTAs.
+MD_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+MD_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+MD_DEVINL void tmem_alloc_2cta(uint32_t* smem_result) {  // one full warp in EACH CTA of the pair, same warp id
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+MD_DEVINL void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// arrive (count 1) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+MD_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
+        ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+MD_DEVINL void mbar_arrive_remote_w(uint64_t* bar, uint32_t rank) {     // warp-collective, one elected lane arrives
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 ra;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "@q mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
+        ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier (peer bit of the address cleared)
+MD_DEVINL void tma_load_2d_2cta_w(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+        ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+MD_DEVINL void umma_ss_2cta_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+MD_DEVINL void tc_commit_2cta_w(uint64_t* bar) {    // arrives on `bar` (same offset) in BOTH CTAs of the pair
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b16 msk;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b16 msk, 3;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], msk;\n\t}\n"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 // Batched forms: ONE election per group of MMAs + the commit that follows (the per-instruction ELECT / R2UR
 // sequence of the single forms costs more issue time than a 32-cycle N=64 MMA takes to execute).
 //   S[tmem_d] = Q K^T over 64 dims: four K=16 MMAs (SS), then commit -> bar
@@ -389,6 +454,8 @@ MD_DEVINL uint64_t f2_exp2_poly(uint64_t x) {
 }
 
 // erf-GELU (HF ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7).
+// (A packed-FFMA2 degree-15 polynomial variant was measured slower in the FFN1 epilogue: the MUFU rcp/ex2 of this
+// form run beside the FMA pipe.)
 MD_DEVINL float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
     const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));

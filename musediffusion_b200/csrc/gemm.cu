@@ -9,6 +9,8 @@
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 // warps 2..9 = epilogue (TMEM -> registers -> bias / GELU / tanh / pos+time -> swizzled smem slab -> TMA store).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "musediff_b200.h"
 
@@ -28,13 +30,14 @@ struct GemmArgs {
     const float* temb;             // [M / L, N] (row stride temb_stride; 0 = one row shared by all sequences)
     int temb_stride;
     void* out;                     // bf16 or fp32 [M, N]
+    int debug_skip;                // tuning experiments only: 1 = no TMA store, 2 = no slab write + no store
 };
 
-template <int BN>
+template <int BN, bool kCta2 = false>
 struct GemmCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kStages = (BN == 256 && !kCta2) ? 4 : 6;
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (kCta2 ? BN / 2 : BN) * BK * 2;   // a CTA pair splits the B tile: 128 W rows per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
     static constexpr int kSlabBytes = 32 * 128;                 // one epilogue warp's staging slab: 32 rows x 128 B
@@ -53,11 +56,18 @@ MD_DEVINL float epi_act(float v) {
 // activation -> 128B-swizzled shared-memory slab (32 rows x 128 B, one per epilogue warp) -> TMA store.  A direct
 // st.global from the TMEM register layout would touch 32 different 128 B lines per warp instruction (one L1TEX
 // wavefront each); the slab + cp.async.bulk.tensor store costs no LSU wavefronts and clips rows >= M / cols >= N.
-template <int BN, int EPI, bool OUT_F32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
-    using Cfg = GemmCfg<BN>;
+// kCta2 = true: launched as clusters of two CTAs (cta_group::2).  A pair computes one 256 x 256 tile: each CTA keeps
+// its own 128 A rows, its own accumulator rows (TMEM) and its own epilogue, but loads only half of the W rows — the
+// UMMA reads operands from both CTAs' shared memory — which halves the per-SM shared-memory traffic of the B operand
+// (the 1-CTA 128x256 mainloop needs 96 B/clk of operand reads + 96 B/clk of TMA fills against a 128 B/clk port).
+template <int BN, int EPI, bool OUT_F32, bool kCta2>
+MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& p) {
+    using Cfg = GemmCfg<BN, kCta2>;
+    const uint32_t cta_rank = kCta2 ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+    const int cta_id = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-scheduler id (pair id)
+    const int n_cta = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int BMT = kCta2 ? 2 * BM : BM;                                   // rows of one scheduled tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -73,7 +83,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int m_tiles = (p.M + BM - 1) / BM;
+    const int m_tiles = (p.M + BMT - 1) / BMT;
     const int num_tiles = n_tiles * m_tiles;
     const int num_kb = (p.K + BK - 1) / BK;
 
@@ -82,18 +92,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
         for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], kCta2 ? 2 : 1);          // pair: one arrival per CTA's producer (leader's barrier is used)
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], kEpiThreads);
+            mbar_init(&tempty_bar[s], kCta2 ? 2 * kEpiThreads : kEpiThreads);   // pair: both CTAs' epilogues release the leader
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if (kCta2) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_slot);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kCta2) cluster_sync_all(); else __syncthreads();     // barriers initialised in BOTH CTAs before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -101,61 +114,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------ TMA producer (whole warp, elected issue)
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
-                tma_load_2d_w(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                tma_load_2d_w(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                if (kCta2) {
+                    // both CTAs credit the LEADER's full barrier: 2 arrivals + the bytes of all four boxes
+                    if (is_leader) mbar_arrive_expect_tx_w(&full_bar[stage], 2 * Cfg::kStageBytes);
+                    else mbar_arrive_remote_w(&full_bar[stage], 0);
+                    tma_load_2d_2cta_w(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BMT + (int)cta_rank * BM);
+                    tma_load_2d_2cta_w(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN + (int)cta_rank * (BN / 2));
+                } else {
+                    mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d_w(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d_w(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                }
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues)
-        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = make_idesc_bf16(BMT, BN);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        if (is_leader) {        // in a pair only the leader CTA issues; its MMAs drive both tensor cores
+            for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
-                const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+                    const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // +32 bytes per UMMA_K step inside the 128B swizzle atom  (encoded >> 4)
-                    umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // +32 bytes per UMMA_K step inside the 128B swizzle atom  (encoded >> 4)
+                        if (kCta2) umma_ss_2cta_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        else umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (kCta2) tc_commit_2cta_w(&empty_bar[stage]); else tc_commit_w(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit_w(&empty_bar[stage]);
-                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                if (kCta2) tc_commit_2cta_w(&tfull_bar[acc]); else tc_commit_w(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            tc_commit_w(&tfull_bar[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
     } else {
         // ------------------------------------------------ epilogue (8 warps)
         const int ew = warp - 2;
         const int q = warp & 3;             // TMEM lane quadrant this warp may access
         const int hsel = ew >> 2;           // which half of the BN columns
+        // Staging: each epilogue warp owns 4 KB.  bf16 output: two 2 KB half-slabs (32 rows x 64 B = 32 columns, 64B
+        // swizzle) used alternately, so the TMA store of chunk c drains while chunk c+1 is produced
+        // (cp.async.bulk.wait_group.read 1).  fp32 output (only the N = 128 projection): one 4 KB slab (32 rows x 128 B).
         uint8_t* slab = sStage + ew * Cfg::kSlabBytes;
-        const uint32_t slab_row = smem_u32(slab) + lane * 128;
-        constexpr int kSlabCols = OUT_F32 ? 32 : 64;          // 128 B of output per row
-        constexpr int kSlabs = (BN / 2) / kSlabCols;
+        constexpr int kChunkCols = 32;
+        constexpr int kChunks = (BN / 2) / kChunkCols;
+        constexpr int kRowBytes = OUT_F32 ? 128 : 64;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t buf = 0;
+        for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int n0 = n_blk * BN;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row0 = m_blk * BM + q * 32;
+            const int row0 = m_blk * BMT + (int)cta_rank * BM + q * 32;
             const int row = row0 + lane;
             int seq_b = 0, seq_l = 0;
             if (EPI == MD_EPI_BIAS_POS_TIME) {
@@ -164,27 +192,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 seq_l = rr - seq_b * p.L;
             }
 #pragma unroll 1
-            for (int sl = 0; sl < kSlabs; ++sl) {
-                const int col0 = hsel * (BN / 2) + sl * kSlabCols;      // column inside the tile
+            for (int c = 0; c < kChunks; ++c) {
+                const int col0 = hsel * (BN / 2) + c * kChunkCols;      // column inside the tile
                 const int n = n0 + col0;
                 if (n >= p.N) break;                                     // warp-uniform
-                float v[kSlabCols];
+                float v[kChunkCols];
                 {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0, r);
                     tc_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (!OUT_F32) {
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0 + 32, r);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[(kSlabCols - 32) + j] = __uint_as_float(r[j]);
-                    }
                 }
                 if (p.bias != nullptr) {
 #pragma unroll
-                    for (int g = 0; g < kSlabCols / 4; ++g) {
+                    for (int g = 0; g < kChunkCols / 4; ++g) {
                         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (n + g * 4 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 4));
                         v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
@@ -192,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 if (EPI == MD_EPI_BIAS_POS_TIME) {
 #pragma unroll
-                    for (int g = 0; g < kSlabCols / 4; ++g) {
+                    for (int g = 0; g < kChunkCols / 4; ++g) {
                         if (n + g * 4 < p.N) {
                             const float4 a = *reinterpret_cast<const float4*>(p.pos + (size_t)seq_l * p.N + n + g * 4);
                             const float4 b = *reinterpret_cast<const float4*>(p.temb + (size_t)seq_b * p.temb_stride + n + g * 4);
@@ -204,33 +226,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < kSlabCols; ++j) v[j] = epi_act<EPI>(v[j]);
-                // the previous TMA store out of this slab must have finished reading shared memory
-                if (lane == 0) tma_store_wait_read<0>();
+                for (int j = 0; j < kChunkCols; ++j) v[j] = epi_act<EPI>(v[j]);
+                if (p.debug_skip == 2) continue;
+                // the TMA store that last used this staging buffer must have finished READING shared memory
+                uint8_t* dst = OUT_F32 ? slab : slab + buf * 2048;
+                if (lane == 0) { if (OUT_F32) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
                 __syncwarp();
+                const uint32_t row_addr = smem_u32(dst) + lane * kRowBytes;
+                if (OUT_F32) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {       // 8 x 16 B chunks per 128 B row, 128B swizzle: chunk ^= row % 8
-                    uint4 u;
-                    if (OUT_F32) {
-                        u = make_uint4(__float_as_uint(v[c * 4 + 0]), __float_as_uint(v[c * 4 + 1]),
-                                       __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3]));
-                    } else {
-                        u = make_uint4(pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                                       pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+                    for (int k = 0; k < 8; ++k) {       // 8 x 16 B per 128 B row, 128B swizzle: chunk ^= row % 8
+                        const uint32_t addr = row_addr + ((k ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(v[k * 4 + 0])),
+                                     "r"(__float_as_uint(v[k * 4 + 1])), "r"(__float_as_uint(v[k * 4 + 2])), "r"(__float_as_uint(v[k * 4 + 3]))
+                                     : "memory");
                     }
-                    const uint32_t addr = slab_row + ((c ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
-                                 : "memory");
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {       // 4 x 16 B per 64 B row, 64B swizzle: chunk ^= (row / 2) % 4
+                        const uint32_t addr = row_addr + ((k ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[k * 8 + 0], v[k * 8 + 1])),
+                                     "r"(pack_bf16x2(v[k * 8 + 2], v[k * 8 + 3])), "r"(pack_bf16x2(v[k * 8 + 4], v[k * 8 + 5])),
+                                     "r"(pack_bf16x2(v[k * 8 + 6], v[k * 8 + 7]))
+                                     : "memory");
+                    }
                 }
                 fence_proxy_async_smem();           // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tmC, slab, n, row0);
+                if (lane == 0 && p.debug_skip == 0) {
+                    tma_store_2d(&tmC, dst, n, row0);
                     tma_store_commit();
                 }
+                buf ^= 1;
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (kCta2 && !is_leader) mbar_arrive_remote(&tempty_bar[acc], 0);      // the MMA issuer lives in the leader CTA
+            else mbar_arrive(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -239,8 +270,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     __syncwarp();
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (kCta2) cluster_sync_all(); else __syncthreads();     // the peer may still read this CTA's smem / signal its barriers
+    if (warp == 1) {
+        if (kCta2) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BN, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
+    gemm_body<BN, EPI, OUT_F32, false>(tmA, tmB, tmC, p);
+}
+
+template <int EPI, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
+    gemm_body<256, EPI, OUT_F32, true>(tmA, tmB, tmC, p);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -265,6 +313,7 @@ static PFN_encodeTiled get_encode_fn() {
 // 2-D row-major [rows, cols] tensor (bf16 or fp32), box = [box_rows, box_cols] with box_cols * elem = 128 B, 128B swizzle.
 int make_tmap_2d(CUtensorMap* tm, const void* base, int is_f32, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                  uint32_t box_rows, uint32_t box_cols) {
+    const bool sw64 = (box_cols * (is_f32 ? 4u : 2u)) == 64u;      // 64-byte box rows use the 64B swizzle, else 128B
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
@@ -272,7 +321,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int is_f32, uint64_t rows, u
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%llu cols=%llu stride=%llu box=%ux%u base=%p)", (int)r,
@@ -332,6 +381,38 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
+template <int EPI, bool OUT_F32>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
+                            cudaStream_t stream) {
+    using Cfg = GemmCfg<256, true>;
+    auto kern = gemm_pair_kernel<EPI, OUT_F32>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+                       "cudaFuncSetAttribute(gemm pair)"))
+            return MD_ERR_CUDA;
+        attr_set = true;
+    }
+    const int n_tiles = (args.N + 255) / 256, m_tiles = (args.M + 255) / 256;
+    int pairs = num_sms() / 2;
+    if (n_tiles * m_tiles < pairs) pairs = n_tiles * m_tiles;
+    kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, args);      // __cluster_dims__(2,1,1)
+    return check_cuda(cudaGetLastError(), "gemm pair launch");
+}
+
+template <bool OUT_F32>
+static int dispatch_epi_pair(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& a,
+                             cudaStream_t s) {
+    switch (epi) {
+        case MD_EPI_BIAS: return launch_gemm_pair<MD_EPI_BIAS, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_GELU: return launch_gemm_pair<MD_EPI_BIAS_GELU, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_TANH: return launch_gemm_pair<MD_EPI_BIAS_TANH, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_POS_TIME: return launch_gemm_pair<MD_EPI_BIAS_POS_TIME, OUT_F32>(tmA, tmB, tmC, a, s);
+    }
+    set_last_error("md_linear_bf16: unknown epilogue %d", epi);
+    return MD_ERR_ARG;
+}
+
 template <int BN, bool OUT_F32>
 static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& a,
                         cudaStream_t s) {
@@ -359,13 +440,19 @@ extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void*
         return MD_ERR_ARG;
     }
     const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
+    // CTA pairs (cta_group::2) for the large regular shapes; MD_GEMM_PAIR=0 forces the single-CTA kernel
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* e = getenv("MD_GEMM_PAIR"); use_pair = e ? atoi(e) : 1; }
+    const bool pair = use_pair && N % 256 == 0 && M >= 1024 && !out_is_f32;
     CUtensorMap tmA, tmB, tmC;
     if (int e = make_tmap_2d(&tmA, A, 0, M, K, K, BM, BK)) return e;
-    if (int e = make_tmap_2d(&tmB, W, 0, N, K, K, BN, BK)) return e;
-    if (int e = make_tmap_2d(&tmC, out, out_is_f32, M, N, N, 32, out_is_f32 ? 32 : 64)) return e;
+    if (int e = make_tmap_2d(&tmB, W, 0, N, K, K, pair ? 128 : BN, BK)) return e;
+    if (int e = make_tmap_2d(&tmC, out, out_is_f32, M, N, N, 32, 32)) return e;
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
     a.bias = bias; a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
+    { const char* e = getenv("MD_GEMM_DEBUG_SKIP"); a.debug_skip = e ? atoi(e) : 0; }
+    if (pair) return dispatch_epi_pair<false>(epilogue, tmA, tmB, tmC, a, stream);
     if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, tmC, a, stream)
                                      : dispatch_epi<256, false>(epilogue, tmA, tmB, tmC, a, stream);
     return out_is_f32 ? dispatch_epi<128, true>(epilogue, tmA, tmB, tmC, a, stream)

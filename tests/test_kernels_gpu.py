@@ -30,7 +30,7 @@ def _gelu_erf(x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 128), (300, 768, 768), (2096, 2304, 768),
-                                   (2096 * 2, 3072, 768), (1000, 768, 3072), (2096, 128, 768), (520, 1024, 1024), (77, 200, 72)])
+                                   (2096 * 2, 3072, 768), (1000, 768, 3072), (2096, 128, 768), (520, 1024, 1024), (77, 200, 72), (1500, 512, 256), (4000, 768, 768)])
 @pytest.mark.parametrize("epi", [_lib.EPI_BIAS, _lib.EPI_BIAS_GELU, _lib.EPI_BIAS_TANH])
 def test_linear(M, N, K, epi):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + epi)
