@@ -39,7 +39,7 @@ template <> struct AttCfg<1> { static constexpr int kThreads = 384, kRegsProduce
 template <> struct AttCfg<2> { static constexpr int kThreads = 640, kRegsProducer = 56, kRegsSoftmax = 104; };   // 128*56 + 512*104 = 60416 <= 640 x 96
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttXchgBytes = (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;   // row-max (double buffered) and row-sum exchange between the two column halves
-constexpr int kAttSmem = 1024 + (2 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 256 + kAttXchgBytes;
+constexpr int kAttSmem = 1024 + (4 + 2 * ATT_STAGES + 2) * ATT_TILE_BYTES + 256 + kAttXchgBytes;   // Q double-buffered across work items; 2 output staging tiles
 // TMEM columns (all 512 used): S and P have separate homes so that S(j+1) = Q K^T can be issued as soon as the softmax
 // warpgroup has READ S(j) into registers — the tensor pipe's latency leaves the softmax critical path.
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
@@ -53,7 +53,8 @@ struct AttArgs {
     int n_kv;           // ceil(L/128)
     int total_work;     // B * NH * n_pairs
     __nv_bfloat16* out; // [B*L, NH*64]
-    long long* trace;   // optional [role 4][event 8][step 64] clock64 stamps of CTA 0 (debug / tuning)
+    int turn_every;     // 1: the two Q tiles alternate on the exp2 phase every key block; 0: only on block 0 (phase offset)
+    long long* trace;   // optional [role 10][event 8][step 64] clock64 stamps of CTA 0 (debug / tuning)
 };
 #define MD_TRACE(role, ev, step)                                                                          \
     do {                                                                                                  \
@@ -86,16 +87,17 @@ MD_DEVINL void turn_pass(int x) {
 
 template <bool kTurns, int kPoly, int kSplit, bool kTrace = false>
 __global__ void __launch_bounds__(AttCfg<kSplit>::kThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, const AttArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                     // 2 tiles
-    uint8_t* sK = smem + 2 * ATT_TILE_BYTES;                // ATT_STAGES tiles
+    uint8_t* sQ = smem;                                     // 2 buffers x 2 tiles: the next work item's Q is prefetched
+    uint8_t* sK = smem + 4 * ATT_TILE_BYTES;                // ATT_STAGES tiles
     uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // ATT_STAGES tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
-    uint64_t* q_full = bars;                // [1]
-    uint64_t* q_empty = bars + 1;           // [1]
-    uint64_t* k_full = bars + 2;            // [STAGES]
+    uint8_t* sO = sV + ATT_STAGES * ATT_TILE_BYTES;         // 2 tiles: normalised output staged for the TMA store
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;                // [2]
+    uint64_t* q_empty = bars + 2;           // [2]
+    uint64_t* k_full = bars + 4;            // [STAGES]
     uint64_t* k_empty = k_full + ATT_STAGES;
     uint64_t* v_full = k_empty + ATT_STAGES;
     uint64_t* v_empty = v_full + ATT_STAGES;
@@ -106,7 +108,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
     uint64_t* s_free = o_empty + 2;            // [2] softmax has read S into registers -> next Q K^T may overwrite it
     uint64_t* p_free = s_free + 2;             // [2] P V of the previous block retired -> P / O may be rewritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
-    float* sMax = reinterpret_cast<float*>(bars) + 64;      // [tile][buf][half][128]   (barriers occupy < 256 B)
+    float* sMax = reinterpret_cast<float*>(bars) + 64;      // [tile][buf][half][128]   (barriers occupy <= 256 B)
     float* sSum = sMax + 2 * 2 * 2 * 128;                   // [tile][half][128]
     constexpr int kTileThreads = 128 * kSplit;              // softmax threads per Q tile
 
@@ -116,8 +118,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 2);                 // both MMA warps (one per Q tile) release the shared stages
+        tma_prefetch_desc(&tmOut);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 2);         // both MMA warps (one per Q tile) release the shared stages
+        }
         for (int s = 0; s < ATT_STAGES; ++s) {
             mbar_init(&k_full[s], 1);
             mbar_init(&k_empty[s], 2);
@@ -150,17 +155,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 const Work wk = decode_work(w, a);
                 const int qt0 = wk.pair * 2;
                 const int n_active = (qt0 + 1 < a.n_qtiles) ? 2 : 1;
-                mbar_wait(q_empty, (wcnt & 1) ^ 1);
-                mbar_arrive_expect_tx_w(q_full, n_active * ATT_TILE_BYTES);
+                const int qb = wcnt & 1;               // Q buffer of this work item
+                mbar_wait_idle(&q_empty[qb], ((wcnt >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx_w(&q_full[qb], n_active * ATT_TILE_BYTES);
                 for (int x = 0; x < n_active; ++x)
-                    tma_load_3d_w(sQ + x * ATT_TILE_BYTES, &tmQKV, q_full, wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
+                    tma_load_3d_w(sQ + (qb * 2 + x) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
                 for (int j = 0; j < a.n_kv; ++j, ++kcnt) {
                     const int st = kcnt % ATT_STAGES;
                     const uint32_t ph = (kcnt / ATT_STAGES) & 1;
-                    mbar_wait(&k_empty[st], ph ^ 1);
+                    mbar_wait_idle(&k_empty[st], ph ^ 1);
                     mbar_arrive_expect_tx_w(&k_full[st], ATT_TILE_BYTES);
                     tma_load_3d_w(sK + st * ATT_TILE_BYTES, &tmQKV, &k_full[st], H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
-                    mbar_wait(&v_empty[st], ph ^ 1);
+                    mbar_wait_idle(&v_empty[st], ph ^ 1);
                     mbar_arrive_expect_tx_w(&v_full[st], ATT_TILE_BYTES);
                     tma_load_3d_w(sV + st * ATT_TILE_BYTES, &tmQKV, &v_full[st], 2 * H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
                 }
@@ -177,7 +183,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0);
             const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0);
             const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0);
-            const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + x * ATT_TILE_BYTES));
             uint32_t wcnt = 0, kcnt = 0;
             uint32_t pcnt = 0;   // P tiles consumed (phase of p_full)
             uint32_t ocnt = 0;   // work items (phase of o_empty)
@@ -185,12 +190,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
                 const bool active = (wk.pair * 2 + x < a.n_qtiles);
-                mbar_wait(q_full, wcnt & 1);
+                const int qb = wcnt & 1;
+                const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + (qb * 2 + x) * ATT_TILE_BYTES));
+                mbar_wait_idle(&q_full[qb], (wcnt >> 1) & 1);
                 {   // S(0)
                     const int st = kcnt % ATT_STAGES;
-                    mbar_wait(&k_full[st], (kcnt / ATT_STAGES) & 1);
+                    mbar_wait_idle(&k_full[st], (kcnt / ATT_STAGES) & 1);
                     if (active) {
-                        if (qcnt > 0) mbar_wait(&s_free[x], (qcnt - 1) & 1);
+                        if (qcnt > 0) mbar_wait_idle(&s_free[x], (qcnt - 1) & 1);
                         ++qcnt;
                         tc_fence_after();
                         umma_qk64_commit_w(tS, qd, make_sdesc_sw128(smem_u32(sK + st * ATT_TILE_BYTES)), idesc_qk, &s_full[x]);
@@ -204,9 +211,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     if (has_next) {
                         // S(j+1): needs only K[j+1] and the softmax warpgroup's READ of S(j)
                         const int st_n = (kcnt + j + 1) % ATT_STAGES;
-                        mbar_wait(&k_full[st_n], ((kcnt + j + 1) / ATT_STAGES) & 1);
+                        mbar_wait_idle(&k_full[st_n], ((kcnt + j + 1) / ATT_STAGES) & 1);
                         if (active) {
-                            mbar_wait(&s_free[x], (qcnt - 1) & 1);
+                            mbar_wait_idle(&s_free[x], (qcnt - 1) & 1);
                             ++qcnt;
                             tc_fence_after();
                             MD_TRACE(x, 0, (int)(wcnt * a.n_kv + j));
@@ -214,11 +221,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                         }
                         tc_commit_w(&k_empty[st_n]);
                     }
-                    mbar_wait(&v_full[st], ph);
+                    mbar_wait_idle(&v_full[st], ph);
                     if (active) {
-                        if (j == 0) mbar_wait(&o_empty[x], (ocnt & 1) ^ 1);   // previous item's O drained
+                        if (j == 0) mbar_wait_idle(&o_empty[x], (ocnt & 1) ^ 1);   // previous item's O drained
                         MD_TRACE(x, 1, (int)(wcnt * a.n_kv + j));
-                        mbar_wait(&p_full[x], pcnt & 1);
+                        mbar_wait_idle(&p_full[x], pcnt & 1);
                         ++pcnt;
                         tc_fence_after();
                         MD_TRACE(x, 2, (int)(wcnt * a.n_kv + j));
@@ -228,7 +235,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     }
                     tc_commit_w(&v_empty[st]);
                 }
-                tc_commit_w(q_empty);
+                tc_commit_w(&q_empty[qb]);
                 kcnt += a.n_kv;
             }
         }
@@ -255,7 +262,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             const int qt = wk.pair * 2 + x;
             if (qt >= a.n_qtiles) {
                 // phantom tile of the last pair: keep the turn-taking handshake in step with the other tile
-                for (int j = 0; j < a.n_kv; ++j) {
+                for (int j = 0; j < (a.turn_every ? a.n_kv : 1); ++j) {
                     turn_wait<kTurns, 2 * kTileThreads>(x);
                     turn_pass<kTurns, 2 * kTileThreads>(x);
                 }
@@ -263,26 +270,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             }
             float m_used = 0.f, l_sum = 0.f;
             for (int j = 0; j < a.n_kv; ++j, ++scnt) {
-                const bool tr = (half == 0 && quad == 0);
-                if (tr) MD_TRACE(2 + x, 0, (int)scnt);
+                const bool tr = (half == 0);
+                if (tr) MD_TRACE(2 + x * 4 + quad, 0, (int)scnt);
                 mbar_wait(&s_full[x], scnt & 1);
                 tc_fence_after();
-                if (tr) MD_TRACE(2 + x, 1, (int)scnt);
-                if (kPoly == 10) {      // timing experiment only: barrier handshakes, no TMEM traffic, no math
-                    tc_fence_before();
-                    mbar_arrive(&s_free[x]);
-                    if (j > 0) { mbar_wait(&p_free[x], fcnt & 1); ++fcnt; tc_fence_after(); }
-                    tc_fence_before();
-                    mbar_arrive(&p_full[x]);
-                    continue;
-                }
+                if (tr) MD_TRACE(2 + x * 4 + quad, 1, (int)scnt);
                 uint32_t s[NG][32];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) tmem_ld32(tS + 32 * g, s[g]);
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&s_free[x]);               // S is in registers: the next Q K^T may overwrite it
-                if (tr) MD_TRACE(2 + x, 2, (int)scnt);
+                if (tr) MD_TRACE(2 + x * 4 + quad, 2, (int)scnt);
                 const int valid = a.L - j * ATT_BKV - half * NC;   // keys of this thread's columns that exist
                 if (valid < NC) {
 #pragma unroll
@@ -311,42 +310,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                     else asm volatile("bar.sync 5, %0;" ::"n"(kTileThreads) : "memory");
                     mrow = fmaxf(mrow, mx[(half ^ 1) * 128 + r]);
                 }
-                if (tr) MD_TRACE(2 + x, 3, (int)scnt);
+                if (tr) MD_TRACE(2 + x * 4 + quad, 3, (int)scnt);
                 const float mb = mrow * kLog2e;        // -inf only if the whole block is masked for this row: impossible (block 0 ...)
+                // lazy rescale decision (the running output lives in TMEM and is only touched after the exponentials,
+                // once P V of block j-1 has retired — the wait is then off the critical path)
+                float f_resc = 1.0f;
+                bool any_resc = false;
                 if (j == 0) {
                     m_used = mb;
                 } else {
-                    mbar_wait(&p_free[x], fcnt & 1);   // P V of block j-1 retired: O and P may be touched
-                    ++fcnt;
-                    tc_fence_after();
                     const bool need = mb > m_used + kRescaleThreshold;
-                    if (__any_sync(0xffffffffu, need)) {
-                        // lazy rescale of the running output (and sum) held in TMEM
-                        const float f = need ? fast_exp2(m_used - mb) : 1.0f;
-                        if (need) m_used = mb;
-                        l_sum *= f;
-#pragma unroll
-                        for (int g = 0; g < OC / 32; ++g) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + 32 * g, o);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
-                            tmem_st32(tO + 32 * g, o);
-                        }
-                    }
+                    any_resc = __any_sync(0xffffffffu, need);
+                    if (need) { f_resc = fast_exp2(m_used - mb); m_used = mb; }
+                    l_sum *= f_resc;
                 }
                 // p = 2^(s log2e - m): packed FFMA2 for the argument, then kPoly of every 8 pairs take the FMA-pipe
                 // polynomial and the rest the MUFU (16 ex2/clk/SM is the binding unit at head dim 64); packed FADD2 sums.
                 uint64_t acc_a = 0, acc_b = 0;     // two independent packed accumulators (bit pattern of +0.0f, +0.0f)
                 const uint64_t l2e2 = f2_pack(kLog2e, kLog2e);
                 const uint64_t negm2 = f2_pack(-m_used, -m_used);
-                if (tr) MD_TRACE(2 + x, 4, (int)scnt);
-                turn_wait<kTurns, 2 * kTileThreads>(x);                                 // my turn on the MUFU pipe
-                if (tr) MD_TRACE(2 + x, 5, (int)scnt);
+                if (tr) MD_TRACE(2 + x * 4 + quad, 4, (int)scnt);
+                const bool turn = (j == 0) || a.turn_every;
+                if (turn) turn_wait<kTurns, 2 * kTileThreads>(x);                       // my turn on the MUFU pipe
+                if (tr) MD_TRACE(2 + x * 4 + quad, 5, (int)scnt);
+                uint32_t pk[NG][16];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
                         const uint64_t arg = f2_fma(f2_pack(__uint_as_float(s[g][2 * c]), __uint_as_float(s[g][2 * c + 1])), l2e2, negm2);
@@ -364,12 +353,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                             p2 = f2_pack(p0, p1);
                         }
                         if (c & 1) acc_b = f2_add(acc_b, p2); else acc_a = f2_add(acc_a, p2);
-                        pk[c] = pack_bf16x2(p0, p1);
+                        pk[g][c] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st16(tP + g * 16, pk);
                 }
-                turn_pass<kTurns, 2 * kTileThreads>(x);                                 // hand the MUFU pipe to the other tile
-                if (tr) MD_TRACE(2 + x, 6, (int)scnt);
+                if (turn) turn_pass<kTurns, 2 * kTileThreads>(x);                       // hand the MUFU pipe to the other tile
+                if (tr) MD_TRACE(2 + x * 4 + quad, 6, (int)scnt);
+                if (j > 0) {
+                    mbar_wait(&p_free[x], fcnt & 1);   // P V of block j-1 retired: O and P may be touched
+                    ++fcnt;
+                    tc_fence_after();
+                    if (any_resc) {
+#pragma unroll
+                        for (int g = 0; g < OC / 32; ++g) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + 32 * g, o);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f_resc);
+                            tmem_st32(tO + 32 * g, o);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) tmem_st16(tP + g * 16, pk[g]);
                 {
                     float q0, q1;
                     f2_unpack(f2_add(acc_a, acc_b), q0, q1);
@@ -378,7 +384,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&p_full[x]);
-                if (tr) MD_TRACE(2 + x, 7, (int)scnt);
+                if (tr) MD_TRACE(2 + x * 4 + quad, 7, (int)scnt);
             }
             // ---- epilogue: O / l -> bf16 -> global
             if (kSplit == 2) {
@@ -397,24 +403,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(&o_empty[x]);
-            const int row = qt * ATT_BQ + r;
-            if (row < a.L) {
+            // Row r -> 128 B of the staging tile (128B swizzle: 16 B chunk ^= row % 8, conflict-free), then ONE bulk
+            // tensor store per tile.  (A direct st.global from the row-per-thread layout touches 32 different lines per
+            // warp instruction and was measured to stall the other tile's TMEM traffic for ~3000 cycles per work item.)
+            // Rows >= L of the last tile are clipped by the tensor map.
+            const bool issuer = (r == 0 && half == 0);
+            if (issuer) tma_store_wait_read<0>();          // the previous item's store has finished reading the tile
+            if (x == 0) asm volatile("bar.sync 6, %0;" ::"n"(kTileThreads) : "memory");
+            else asm volatile("bar.sync 7, %0;" ::"n"(kTileThreads) : "memory");
+            {
                 const float inv = 1.0f / l_sum;
-                __nv_bfloat16* dst = a.out + ((size_t)wk.b * a.L + row) * H + wk.h * ATT_DH + half * OC;
+                const uint32_t row_addr = smem_u32(sO + x * ATT_TILE_BYTES) + r * 128;
 #pragma unroll
                 for (int gg = 0; gg < OC / 32; ++gg)
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 u;
-                        u.x = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 0]) * inv, __uint_as_float(o[gg][g * 8 + 1]) * inv);
-                        u.y = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 2]) * inv, __uint_as_float(o[gg][g * 8 + 3]) * inv);
-                        u.z = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 4]) * inv, __uint_as_float(o[gg][g * 8 + 5]) * inv);
-                        u.w = pack_bf16x2(__uint_as_float(o[gg][g * 8 + 6]) * inv, __uint_as_float(o[gg][g * 8 + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + gg * 32 + g * 8) = u;
+                        const int chunk = half * (OC / 8) + gg * 4 + g;
+                        const uint32_t addr = row_addr + ((chunk ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                                     "r"(pack_bf16x2(__uint_as_float(o[gg][g * 8 + 0]) * inv, __uint_as_float(o[gg][g * 8 + 1]) * inv)),
+                                     "r"(pack_bf16x2(__uint_as_float(o[gg][g * 8 + 2]) * inv, __uint_as_float(o[gg][g * 8 + 3]) * inv)),
+                                     "r"(pack_bf16x2(__uint_as_float(o[gg][g * 8 + 4]) * inv, __uint_as_float(o[gg][g * 8 + 5]) * inv)),
+                                     "r"(pack_bf16x2(__uint_as_float(o[gg][g * 8 + 6]) * inv, __uint_as_float(o[gg][g * 8 + 7]) * inv))
+                                     : "memory");
                     }
+            }
+            fence_proxy_async_smem();
+            if (x == 0) asm volatile("bar.sync 6, %0;" ::"n"(kTileThreads) : "memory");
+            else asm volatile("bar.sync 7, %0;" ::"n"(kTileThreads) : "memory");
+            if (issuer) {
+                tma_store_3d(&tmOut, sO + x * ATT_TILE_BYTES, wk.h * ATT_DH, qt * ATT_BQ, wk.b);
+                tma_store_commit();
             }
         }
     }
+    if (warp >= 4 && (threadIdx.x & 127) == 0) tma_store_wait_read<0>();   // staging tiles must outlive the bulk stores' reads
     __syncwarp();
     if (kTurns && warp >= 4 && warp < 4 + 4 * kSplit) turn_wait<kTurns, 2 * kTileThreads>(0);   // absorb tile 1's final hand-over
     tc_fence_before();
@@ -441,21 +464,25 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
     a.trace = nullptr;
     if (const char* tp = getenv("MD_ATT_TRACE_PTR")) a.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
-    typedef void (*KernelFn)(const CUtensorMap, const AttArgs);
+    CUtensorMap tmo;
+    if (int e = make_tmap_bf16_3d(&tmo, out, H, L, B, H, (uint64_t)L * H, 64, 128)) return e;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const AttArgs);
     static KernelFn kern = nullptr;
     static int threads = 0;
+    static int turn_every = 1;
     if (kern == nullptr) {
         // tuning switches (defaults are the measured best): MD_ATT_TURNS = MUFU turn-taking between the two Q tiles,
         // MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU,
         // MD_ATT_SPLIT = softmax threads per S row (1 or 2)
         const char* e = getenv("MD_ATT_TURNS");
-        const int turns = e ? atoi(e) : 1;
+        const int turns = e ? atoi(e) : 1;     // 0 none, 1 every key block, 2 first block of a work item only
+        turn_every = (turns == 1);
         e = getenv("MD_ATT_POLY");
         const int poly = e ? atoi(e) : 3;
         e = getenv("MD_ATT_SPLIT");
         const int split = e ? atoi(e) : 1;
 #define MD_ATT_PICK(T_, S_)                                                                                               \
-    (poly == 10 ? attention_kernel<T_, 10, S_> : poly == 9 ? attention_kernel<T_, 9, S_> : poly >= 4 ? attention_kernel<T_, 4, S_> : poly == 3 ? attention_kernel<T_, 3, S_> \
+    (poly == 9 ? attention_kernel<T_, 9, S_> : poly >= 4 ? attention_kernel<T_, 4, S_> : poly == 3 ? attention_kernel<T_, 3, S_> \
      : poly == 2 ? attention_kernel<T_, 2, S_> : attention_kernel<T_, 0, S_>)
         if (split == 2) kern = turns ? MD_ATT_PICK(true, 2) : MD_ATT_PICK(false, 2);
         else kern = turns ? MD_ATT_PICK(true, 1) : MD_ATT_PICK(false, 1);
@@ -471,7 +498,8 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
             return MD_ERR_CUDA;
         }
     }
+    a.turn_every = turn_every;
     const int grid = a.total_work < num_sms() ? a.total_work : num_sms();
-    kern<<<grid, threads, kAttSmem, stream>>>(tm, a);
+    kern<<<grid, threads, kAttSmem, stream>>>(tm, tmo, a);
     return check_cuda(cudaGetLastError(), "attention launch");
 }

@@ -225,8 +225,13 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                         }
                     }
                 }
+                if (EPI == MD_EPI_BIAS_GELU) {
 #pragma unroll
-                for (int j = 0; j < kChunkCols; ++j) v[j] = epi_act<EPI>(v[j]);
+                    for (int j = 0; j < kChunkCols; j += 2) f2_unpack(gelu_erf_x2(f2_pack(v[j], v[j + 1])), v[j], v[j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kChunkCols; ++j) v[j] = epi_act<EPI>(v[j]);
+                }
                 if (p.debug_skip == 2) continue;
                 // the TMA store that last used this staging buffer must have finished READING shared memory
                 uint8_t* dst = OUT_F32 ? slab : slab + buf * 2048;
