@@ -39,7 +39,7 @@ template <> struct AttCfg<1> { static constexpr int kThreads = 384, kRegsProduce
 template <> struct AttCfg<2> { static constexpr int kThreads = 640, kRegsProducer = 56, kRegsSoftmax = 104; };   // 128*56 + 512*104 = 60416 <= 640 x 96
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // every smem tile is 128 rows x 128 B
 constexpr int kAttXchgBytes = (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;   // row-max (double buffered) and row-sum exchange between the two column halves
-constexpr int kAttSmem = 1024 + (4 + 2 * ATT_STAGES + 2) * ATT_TILE_BYTES + 256 + kAttXchgBytes;   // Q double-buffered across work items; 2 output staging tiles
+constexpr int kAttSmem = 1024 + (4 + 2 * ATT_STAGES + 2) * ATT_TILE_BYTES + 512 + kAttXchgBytes;   // Q double-buffered across work items; 2 output staging tiles
 // TMEM columns (all 512 used): S and P have separate homes so that S(j+1) = Q K^T can be issued as soon as the softmax
 // warpgroup has READ S(j) into registers — the tensor pipe's latency leaves the softmax critical path.
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
@@ -106,9 +106,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     uint64_t* o_full = p_full + 2;             // [2]
     uint64_t* o_empty = o_full + 2;            // [2]
     uint64_t* s_free = o_empty + 2;            // [2] softmax has read S into registers -> next Q K^T may overwrite it
-    uint64_t* p_free = s_free + 2;             // [2] P V of the previous block retired -> P / O may be rewritten
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
-    float* sMax = reinterpret_cast<float*>(bars) + 64;      // [tile][buf][half][128]   (barriers occupy <= 256 B)
+    uint64_t* p_free = s_free + 2;             // [2] last key block only: P V of block n-2 retired (earlier blocks learn it from s_full(j+1))
+    uint64_t* sink = p_free + 2;               // [2] commit target nobody waits on
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sink + 2);
+    float* sMax = reinterpret_cast<float*>(bars) + 128;     // [tile][buf][half][128]   (barriers occupy < 512 B)
     float* sSum = sMax + 2 * 2 * 2 * 128;                   // [tile][half][128]
     constexpr int kTileThreads = 128 * kSplit;              // softmax threads per Q tile
 
@@ -136,6 +137,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             mbar_init(&o_empty[x], kTileThreads);
             mbar_init(&s_free[x], kTileThreads);
             mbar_init(&p_free[x], 1);
+            mbar_init(&sink[x], 1);
         }
         fence_barrier_init();
     }
@@ -221,6 +223,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         }
                         tc_commit_w(&k_empty[st_n]);
                     }
+                    if (active && !has_next && j > 0) tc_commit_w(&p_free[x]);     // tracks P V(n-2) for the last block's softmax
                     mbar_wait_idle(&v_full[st], ph);
                     if (active) {
                         if (j == 0) mbar_wait_idle(&o_empty[x], (ocnt & 1) ^ 1);   // previous item's O drained
@@ -230,7 +233,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         tc_fence_after();
                         MD_TRACE(x, 2, (int)(wcnt * a.n_kv + j));
                         umma_pv128_commit_w(tO, tP, make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES)), idesc_pv, j > 0 ? 1u : 0u,
-                                            has_next ? &p_free[x] : &o_full[x]);
+                                            has_next ? &sink[x] : &o_full[x]);
                         if (!has_next) ++ocnt;
                     }
                     tc_commit_w(&v_empty[st]);
@@ -268,12 +271,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 }
                 continue;
             }
-            float m_used = 0.f, l_sum = 0.f;
+            float m_used = -INFINITY, l_sum = 0.f;
+            // One mbarrier wait per key block: S(j+1)'s commit also covers P V(j-1) (tcgen05.commit tracks every earlier
+            // MMA of the issuing thread), so waiting for it after the exponentials of block j both frees P / O for
+            // rewriting and pre-pays the wait at the top of block j+1.
+            mbar_wait(&s_full[x], scnt & 1);
+            tc_fence_after();
             for (int j = 0; j < a.n_kv; ++j, ++scnt) {
                 const bool tr = (half == 0);
                 if (tr) MD_TRACE(2 + x * 4 + quad, 0, (int)scnt);
-                mbar_wait(&s_full[x], scnt & 1);
-                tc_fence_after();
                 if (tr) MD_TRACE(2 + x * 4 + quad, 1, (int)scnt);
                 uint32_t s[NG][32];
 #pragma unroll
@@ -314,16 +320,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const float mb = mrow * kLog2e;        // -inf only if the whole block is masked for this row: impossible (block 0 ...)
                 // lazy rescale decision (the running output lives in TMEM and is only touched after the exponentials,
                 // once P V of block j-1 has retired — the wait is then off the critical path)
-                float f_resc = 1.0f;
-                bool any_resc = false;
-                if (j == 0) {
-                    m_used = mb;
-                } else {
-                    const bool need = mb > m_used + kRescaleThreshold;
-                    any_resc = __any_sync(0xffffffffu, need);
-                    if (need) { f_resc = fast_exp2(m_used - mb); m_used = mb; }
-                    l_sum *= f_resc;
-                }
+                // (branch-free: block 0 starts from m_used = -inf, so it always "rescales" an empty sum by 2^-inf = 0)
+                const bool need = mb > m_used + kRescaleThreshold;
+                const bool any_resc = __any_sync(0xffffffffu, need) && j > 0;
+                const float f_resc = need ? fast_exp2(m_used - mb) : 1.0f;
+                m_used = need ? mb : m_used;
+                l_sum *= f_resc;
                 // p = 2^(s log2e - m): packed FFMA2 for the argument, then kPoly of every 8 pairs take the FMA-pipe
                 // polynomial and the rest the MUFU (16 ex2/clk/SM is the binding unit at head dim 64); packed FADD2 sums.
                 uint64_t acc_a = 0, acc_b = 0;     // two independent packed accumulators (bit pattern of +0.0f, +0.0f)
@@ -358,9 +360,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 }
                 if (turn) turn_pass<kTurns, 2 * kTileThreads>(x);                       // hand the MUFU pipe to the other tile
                 if (tr) MD_TRACE(2 + x * 4 + quad, 6, (int)scnt);
-                if (j > 0) {
-                    mbar_wait(&p_free[x], fcnt & 1);   // P V of block j-1 retired: O and P may be touched
-                    ++fcnt;
+                {
+                    if (j + 1 < a.n_kv) {
+                        mbar_wait(&s_full[x], (scnt + 1) & 1);      // S(j+1) done => P V(j-1) retired: O and P may be touched
+                    } else if (j > 0) {
+                        mbar_wait(&p_free[x], fcnt & 1);
+                        ++fcnt;
+                    }
                     tc_fence_after();
                     if (any_resc) {
 #pragma unroll
@@ -475,21 +481,21 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
         // MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU,
         // MD_ATT_SPLIT = softmax threads per S row (1 or 2)
         const char* e = getenv("MD_ATT_TURNS");
-        const int turns = e ? atoi(e) : 1;     // 0 none, 1 every key block, 2 first block of a work item only
+        const int turns = e ? atoi(e) : 0;     // 0 none, 1 every key block, 2 first block of a work item only
         turn_every = (turns == 1);
         e = getenv("MD_ATT_POLY");
-        const int poly = e ? atoi(e) : 3;
+        const int poly = e ? atoi(e) : 2;
         e = getenv("MD_ATT_SPLIT");
         const int split = e ? atoi(e) : 1;
 #define MD_ATT_PICK(T_, S_)                                                                                               \
     (poly == 9 ? attention_kernel<T_, 9, S_> : poly >= 4 ? attention_kernel<T_, 4, S_> : poly == 3 ? attention_kernel<T_, 3, S_> \
-     : poly == 2 ? attention_kernel<T_, 2, S_> : attention_kernel<T_, 0, S_>)
+     : poly == 2 ? attention_kernel<T_, 2, S_> : poly == 1 ? attention_kernel<T_, 1, S_> : attention_kernel<T_, 0, S_>)
         if (split == 2) kern = turns ? MD_ATT_PICK(true, 2) : MD_ATT_PICK(false, 2);
         else kern = turns ? MD_ATT_PICK(true, 1) : MD_ATT_PICK(false, 1);
 #undef MD_ATT_PICK
         if (getenv("MD_ATT_TRACE_PTR")) {      // timeline tracing build of the selected split (tools/att_trace.py)
             if (split == 2) kern = turns ? attention_kernel<true, 0, 2, true> : attention_kernel<false, 0, 2, true>;
-            else kern = turns ? attention_kernel<true, 3, 1, true> : attention_kernel<false, 3, 1, true>;
+            else kern = turns ? attention_kernel<true, 2, 1, true> : attention_kernel<false, 2, 1, true>;
         }
         threads = split == 2 ? AttCfg<2>::kThreads : AttCfg<1>::kThreads;
         if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
