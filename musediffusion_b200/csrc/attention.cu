@@ -15,9 +15,10 @@
 //
 // Roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0: TMA producer, warp 1: TMEM owner + MMA issuer of Q
 // tile 0, warp 2: MMA issuer of Q tile 1, warp 3: idle}, warpgroup 1 = softmax/correction/epilogue for Q tile 0, warpgroup 2 = same for Q tile 1.
-// setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (a full S row lives in registers), and a
-// pair of named barriers makes the two softmax warpgroups take turns on the exp2 (MUFU) phase: at head dim 64 the
-// MUFU pipe, not the tensor pipe, is the binding unit, so its phases must never idle or overlap.
+// setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (a full S row lives in registers).  At head dim
+// 64 the MUFU / FMA / ALU mix of the softmax, not the tensor pipe, is the binding resource; a pair of named barriers
+// can make the two softmax warpgroups take turns on the exp2 phase (MD_ATT_TURNS, off by default: measured slower once
+// the P V wait had been moved behind the exponentials).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -107,8 +108,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     uint64_t* o_empty = o_full + 2;            // [2]
     uint64_t* s_free = o_empty + 2;            // [2] softmax has read S into registers -> next Q K^T may overwrite it
     uint64_t* p_free = s_free + 2;             // [2] last key block only: P V of block n-2 retired (earlier blocks learn it from s_full(j+1))
-    uint64_t* sink = p_free + 2;               // [2] commit target nobody waits on
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sink + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
     float* sMax = reinterpret_cast<float*>(bars) + 128;     // [tile][buf][half][128]   (barriers occupy < 512 B)
     float* sSum = sMax + 2 * 2 * 2 * 128;                   // [tile][half][128]
     constexpr int kTileThreads = 128 * kSplit;              // softmax threads per Q tile
@@ -137,7 +137,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             mbar_init(&o_empty[x], kTileThreads);
             mbar_init(&s_free[x], kTileThreads);
             mbar_init(&p_free[x], 1);
-            mbar_init(&sink[x], 1);
         }
         fence_barrier_init();
     }
@@ -232,9 +231,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         ++pcnt;
                         tc_fence_after();
                         MD_TRACE(x, 2, (int)(wcnt * a.n_kv + j));
-                        umma_pv128_commit_w(tO, tP, make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES)), idesc_pv, j > 0 ? 1u : 0u,
-                                            has_next ? &sink[x] : &o_full[x]);
-                        if (!has_next) ++ocnt;
+                        const uint64_t vd = make_sdesc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
+                        if (has_next) {
+                            umma_pv128_w(tO, tP, vd, idesc_pv, j > 0 ? 1u : 0u);    // covered by the commit behind Q K^T(j+2)
+                        } else {
+                            umma_pv128_commit_w(tO, tP, vd, idesc_pv, j > 0 ? 1u : 0u, &o_full[x]);
+                            ++ocnt;
+                        }
                     }
                     tc_commit_w(&v_empty[st]);
                 }
