@@ -151,7 +151,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     if (warp == 0) {
         // =========================================================== TMA producer (whole warp, elected issue)
         {
-            uint32_t wcnt = 0, kcnt = 0;
+            uint32_t wcnt = 0;
+            uint32_t st = 0, ph = 0;               // K/V ring position, carried across work items
             for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++wcnt) {
                 const Work wk = decode_work(w, a);
                 const int qt0 = wk.pair * 2;
@@ -161,15 +162,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 mbar_arrive_expect_tx_w(&q_full[qb], n_active * ATT_TILE_BYTES);
                 for (int x = 0; x < n_active; ++x)
                     tma_load_3d_w(sQ + (qb * 2 + x) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], wk.h * ATT_DH, (qt0 + x) * ATT_BQ, wk.b);
-                for (int j = 0; j < a.n_kv; ++j, ++kcnt) {
-                    const int st = kcnt % ATT_STAGES;
-                    const uint32_t ph = (kcnt / ATT_STAGES) & 1;
+                for (int j = 0; j < a.n_kv; ++j) {
                     mbar_wait_idle(&k_empty[st], ph ^ 1);
                     mbar_arrive_expect_tx_w(&k_full[st], ATT_TILE_BYTES);
                     tma_load_3d_w(sK + st * ATT_TILE_BYTES, &tmQKV, &k_full[st], H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
                     mbar_wait_idle(&v_empty[st], ph ^ 1);
                     mbar_arrive_expect_tx_w(&v_full[st], ATT_TILE_BYTES);
                     tma_load_3d_w(sV + st * ATT_TILE_BYTES, &tmQKV, &v_full[st], 2 * H + wk.h * ATT_DH, j * ATT_BKV, wk.b);
+                    if (++st == ATT_STAGES) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -184,7 +184,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             const uint32_t tS = tmem_base + (x ? TM_S1 : TM_S0);
             const uint32_t tP = tmem_base + (x ? TM_P1 : TM_P0);
             const uint32_t tO = tmem_base + (x ? TM_O1 : TM_O0);
-            uint32_t wcnt = 0, kcnt = 0;
+            uint32_t wcnt = 0;
+            uint32_t st = 0, ph = 0;   // K/V ring position of key block j, carried across work items
             uint32_t pcnt = 0;   // P tiles consumed (phase of p_full)
             uint32_t ocnt = 0;   // work items (phase of o_empty)
             uint32_t qcnt = 0;   // Q K^T issued (phase of s_free)
@@ -195,8 +196,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const uint64_t qd = make_sdesc_sw128(smem_u32(sQ + (qb * 2 + x) * ATT_TILE_BYTES));
                 mbar_wait_idle(&q_full[qb], (wcnt >> 1) & 1);
                 {   // S(0)
-                    const int st = kcnt % ATT_STAGES;
-                    mbar_wait_idle(&k_full[st], (kcnt / ATT_STAGES) & 1);
+                    mbar_wait_idle(&k_full[st], ph);
                     if (active) {
                         if (qcnt > 0) mbar_wait_idle(&s_free[x], (qcnt - 1) & 1);
                         ++qcnt;
@@ -206,13 +206,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     tc_commit_w(&k_empty[st]);
                 }
                 for (int j = 0; j < a.n_kv; ++j) {
-                    const int st = (kcnt + j) % ATT_STAGES;
-                    const uint32_t ph = ((kcnt + j) / ATT_STAGES) & 1;
                     const bool has_next = (j + 1 < a.n_kv);
+                    uint32_t st_n = st + 1, ph_n = ph;
+                    if (st_n == ATT_STAGES) { st_n = 0; ph_n ^= 1; }
                     if (has_next) {
                         // S(j+1): needs only K[j+1] and the softmax warpgroup's READ of S(j)
-                        const int st_n = (kcnt + j + 1) % ATT_STAGES;
-                        mbar_wait_idle(&k_full[st_n], ((kcnt + j + 1) / ATT_STAGES) & 1);
+                        mbar_wait_idle(&k_full[st_n], ph_n);
                         if (active) {
                             mbar_wait_idle(&s_free[x], (qcnt - 1) & 1);
                             ++qcnt;
@@ -240,9 +239,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         }
                     }
                     tc_commit_w(&v_empty[st]);
+                    st = st_n;
+                    ph = ph_n;
                 }
                 tc_commit_w(&q_empty[qb]);
-                kcnt += a.n_kv;
             }
         }
     }
