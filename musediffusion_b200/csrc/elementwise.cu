@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const float* E, const
 // ----------------------------------------------------------------------------------------------
 // LayerNorm (bf16 in/out, fp32 statistics), one warp per row
 // ----------------------------------------------------------------------------------------------
-template <int VEC>  // VEC 16-byte vectors (8 bf16) per lane: H = 256 * VEC
+template <int VEC, bool kHoist>  // VEC 16-byte vectors (8 bf16) per lane: H = 256 * VEC; kHoist: gamma / beta live in registers
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in,
                                                         const __nv_bfloat16* __restrict__ resid,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -504,6 +504,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // gamma / beta are the same for every row: re-loading them per row (6 KB against 4.6 KB of activations) made the
+    // L1 data pipe, not HBM, the limiter once the SM clock drops under the power cap
+    float hg[kHoist ? VEC * 8 : 1], hb[kHoist ? VEC * 8 : 1];
+    if (kHoist) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int c = (j * 32 + lane) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { hg[j * 8 + e] = gamma[c + e]; hb[j * 8 + e] = beta[c + e]; }
+        }
+    }
     for (int64_t row = warp_global; row < M; row += nwarps) {
         const __nv_bfloat16* p = in + row * H;
         float v[VEC * 8];
@@ -545,13 +556,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const int c = (j * 32 + lane) * 8;
-            const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float y[8];
+            if (kHoist) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = fmaf((v[j * 8 + e] - mean) * rstd, gg[e], bb[e]);
+                for (int e = 0; e < 8; ++e) y[e] = fmaf((v[j * 8 + e] - mean) * rstd, hg[j * 8 + e], hb[j * 8 + e]);
+            } else {
+                const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = fmaf((v[j * 8 + e] - mean) * rstd, gg[e], bb[e]);
+            }
             *reinterpret_cast<uint4*>(out + row * H + c) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
                                                                      pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
         }
@@ -684,15 +700,20 @@ extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const vo
     const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(resid);
+    static const bool hoist = getenv("MD_LN_HOIST") ? atoi(getenv("MD_LN_HOIST")) != 0 : true;
     switch (H / 256) {
-        case 1: layernorm_kernel<1><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 2: layernorm_kernel<2><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 3: layernorm_kernel<3><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 4: layernorm_kernel<4><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 5: layernorm_kernel<5><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 6: layernorm_kernel<6><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        case 7: layernorm_kernel<7><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
-        default: layernorm_kernel<8><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 1: layernorm_kernel<1, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 2: layernorm_kernel<2, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 3: if (hoist) layernorm_kernel<3, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M);
+                else layernorm_kernel<3, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M);
+                break;
+        case 4: if (hoist) layernorm_kernel<4, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M);
+                else layernorm_kernel<4, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M);
+                break;
+        case 5: layernorm_kernel<5, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 6: layernorm_kernel<6, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        case 7: layernorm_kernel<7, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
+        default: layernorm_kernel<8, false><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
     }
     return check_cuda(cudaGetLastError(), "layernorm launch");
 }

@@ -209,7 +209,8 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                     for (int g = 0; g < kChunkCols / 4; ++g) {
                         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (n + g * 4 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 4));
-                        v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+                        f2_unpack(f2_add(f2_pack(v[g * 4 + 0], v[g * 4 + 1]), f2_pack(b.x, b.y)), v[g * 4 + 0], v[g * 4 + 1]);   // FADD2
+                        f2_unpack(f2_add(f2_pack(v[g * 4 + 2], v[g * 4 + 3]), f2_pack(b.z, b.w)), v[g * 4 + 2], v[g * 4 + 3]);
                     }
                 }
                 if (EPI == MD_EPI_BIAS_POS_TIME) {
