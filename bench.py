@@ -358,10 +358,15 @@ def main():
         args.no_cpu_baseline = True      # the CPU port sample is sized for the base config only
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        import torch.distributed as torch_dist
+        if torch_dist.is_available() and torch_dist.is_initialized():
+            torch_dist.destroy_process_group()
 
 
 if __name__ == "__main__":

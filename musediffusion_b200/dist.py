@@ -23,7 +23,16 @@ def setup(backend=None):
 
 def barrier():
     if dist.is_initialized():
-        dist.barrier()
+        if dist.get_backend() == "nccl":
+            dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            dist.barrier()
+
+
+def shutdown():
+    """Tear the process group down (no-op when single-process)."""
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def shard_range(n, rank, world):
