@@ -136,6 +136,31 @@ int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t ste
 int md_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t step_counter, int64_t elem_offset, float top_p,
                    cudaStream_t stream);
 
+
+/* ---- token-level half of the post-sampling decode, batched -------------------------
+ * What SequenceToMidi.decode does before the MIDI writer (MuseDiffusion/utils/decode_util.py:207-214) for every row of
+ * a sampled batch: split_meta_midi (:192-199: meta / note split from the mask), remove_padding (:72-82: cut after the
+ * first EOS), restore_chord (:84-141: splice the meta's (position, chord) pairs back in), validate_once (:143-155) and,
+ * if strict != 0, validate_rigidly (:157-184).  Replaces the per-row Python of batch_decode_seq2seq /
+ * batch_decode_generation (:259-384) up to the point where miditoolkit takes over.
+ *   tokens, mask  int32 [B, L] (sampled ids; the ORIGINAL input mask: 0 over meta + first EOS)
+ *   status        int32 [B]     MD_DECODE_* below (the reference raises SequenceToMidiError(msg) for 1..4 and lets an
+ *                               IndexError escape — aborting the run — for 5)
+ *   note_len      int32 [B]     length of the restored note sequence (0 when it does not exist)
+ *   notes         int32 [B, 2L] restored note sequence, zero padded
+ *   meta          int32 [B, 11] the 11 meta tokens handed to the MIDI writer */
+enum {
+    MD_DECODE_OK = 0,
+    MD_DECODE_NO_EOS = 1,             /* "NO EOS TOKEN" */
+    MD_DECODE_RESTORE_FAILED = 2,     /* "RESTORE_CHORD FROM META FAILED" */
+    MD_DECODE_VALIDATION_FAILED = 3,  /* "VALIDATION OF SEQUENCE FAILED" */
+    MD_DECODE_STRICT_FAILED = 4,      /* "STRICT VALIDATION OF SEQUENCE FAILED" */
+    MD_DECODE_INDEX_ERROR = 5,        /* the reference's numpy indexing raises IndexError here */
+    MD_DECODE_TOO_LONG = 6            /* restored sequence longer than 2L (degenerate meta; the reference has no bound) */
+};
+int md_decode_prepare(const int32_t* tokens, const int32_t* mask, int B, int L, int strict, int32_t* status,
+                      int32_t* note_len, int32_t* notes, int32_t* meta, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

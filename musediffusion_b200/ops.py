@@ -311,3 +311,19 @@ def fill_normal(shape, device, seed=0, step_counter=0, elem_offset=0, top_p=0.0)
     call("md_fill_normal", _p(out), out.numel(), int(seed), int(step_counter), int(elem_offset), float(top_p),
          _stream())
     return out
+
+
+def decode_prepare(tokens, mask, strict=False):
+    """md_decode_prepare: the token-level half of SequenceToMidi.decode (decode_util.py:72-199) for a whole batch.
+    tokens / mask: integer [B, L] CUDA tensors.  Returns (status [B], note_len [B], notes [B, 2L], meta [B, 11]), int32."""
+    B, L = tokens.shape
+    tok = tokens.to(torch.int32).contiguous()
+    msk = mask.to(torch.int32).contiguous()
+    dev = tok.device
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    note_len = torch.empty((B,), dtype=torch.int32, device=dev)
+    notes = torch.empty((B, 2 * L), dtype=torch.int32, device=dev)
+    meta = torch.empty((B, 11), dtype=torch.int32, device=dev)
+    call("md_decode_prepare", _p(tok), _p(msk), B, L, 1 if strict else 0, _p(status), _p(note_len), _p(notes), _p(meta),
+         _stream())
+    return status, note_len, notes, meta

@@ -82,6 +82,8 @@ def create_parser():
         sp.add_argument("--sample_seed", type=int, default=105)
         sp.add_argument("--clip_denoised", type=lambda s: s.lower() in ("1", "true", "yes"), default=True)
         sp.add_argument("--input_npz", default=None, help="npz with input_ids/input_mask [N, L] (else synthetic)")
+        sp.add_argument("--strict_validation", action="store_true",
+                        help="also run validate_rigidly (the reference does when it computes metrics, run/sample.py:240)")
         if name == "modification":
             sp.add_argument("--strength", type=float, default=0.75)
             sp.add_argument("--num_batches", type=int, default=1)
@@ -92,7 +94,7 @@ def create_parser():
 
 def main(argv=None):
     args = create_parser().parse_args(argv)
-    from . import dist
+    from . import decode_util, dist
     rank, world, dev = dist.setup()
     targs = load_training_args(args.model_path)
     model, diffusion = create_model_and_diffusion(targs)
@@ -123,10 +125,26 @@ def main(argv=None):
         tok = sample_batch(model, diffusion, model_emb, cond, args.mode, args.step, targs.diffusion_steps,
                            strength=getattr(args, "strength", 0.75), top_p=args.top_p, clamp_step=args.clamp_step,
                            clip_denoised=args.clip_denoised, device=dev)
-        tokens.append((bi, tok.cpu().numpy()))
+        # token-level half of decode_batch (utils/decode_util.py:233-384), one launch for the whole batch, on the rank
+        # that sampled it: the reference does this row by row, rank after rank (run/sample.py:222-294)
+        prep = decode_util.prepare_batch(tok, cond["input_mask"].to(dev), strict_validation=args.strict_validation)
+        tokens.append((bi, tok.cpu().numpy(), prep.status, [n for n in prep.note_seqs], [m for m in prep.metas]))
     gathered = dist.gather_objects(tokens)
     if rank == 0:
-        flat = [t for _, t in sorted(sum(gathered, []), key=lambda p: p[0])]
+        rows = sorted(sum(gathered, []), key=lambda p: p[0])
+        flat = [t for _, t, _, _, _ in rows]
         np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
-        print("### Total takes %.2fs; %d sequences -> %s" % (time.time() - tic, sum(len(t) for t in flat), out_dir))
+        status = np.concatenate([st for _, _, st, _, _ in rows])
+        np.save(os.path.join(out_dir, "decode_status.npy"), status)
+        valid = 0
+        for bi, _, st, note_seqs, metas in rows:                  # same warnings / counts as batch_decode_* prints
+            for index in np.nonzero(st != decode_util.OK)[0]:
+                print("<Warning> Batch %d Index %d (Original: %d) - Generation Failure: %s"
+                      % (bi, index, bi * args.batch_size + index, decode_util.STATUS_TEXT[int(st[index])]))
+            for index in np.nonzero(st == decode_util.OK)[0]:     # what decode_event_sequence (:201-205) would be handed
+                np.savez(os.path.join(out_dir, "%07d_batch%05d_%04d.notes.npz" % (bi * args.batch_size + index, bi, index)),
+                         note_seq=note_seqs[index], encoded_meta=metas[index])
+            valid += int((st == decode_util.OK).sum())
+        print("### Total takes %.2fs; %d sequences (%d valid) -> %s"
+              % (time.time() - tic, sum(len(t) for t in flat), valid, out_dir))
     dist.barrier()

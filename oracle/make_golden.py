@@ -218,9 +218,41 @@ def golden_meta_prefix():
     print("meta_batch.npz", b["input_ids"][0, :30].tolist())
 
 
+def golden_decode_prepare():
+    """the reference's own SequenceToMidi (decode_util.py:57-199) on the rows above."""
+    from MuseDiffusion.utils.decode_util import SequenceToMidi, SequenceToMidiError
+    codes = {"NO EOS TOKEN": 1, "RESTORE_CHORD FROM META FAILED": 2, "VALIDATION OF SEQUENCE FAILED": 3,
+             "STRICT VALIDATION OF SEQUENCE FAILED": 4}
+    from decode_oracle import decode_cases
+    tokens, masks = decode_cases()
+    B, L = tokens.shape
+    out = {}
+    for strict in (0, 1):
+        dec = SequenceToMidi(strict_validation=bool(strict))
+        status = np.zeros((B,), np.int32); note_len = np.zeros((B,), np.int32)
+        notes = np.zeros((B, 2 * L), np.int32); meta = np.zeros((B, 11), np.int32)
+        for b in range(B):
+            ns = mt = None
+            try:
+                ns, mt = dec.split_meta_midi(tokens[b], masks[b])
+                dec.validate_generated_sequence(ns)
+            except SequenceToMidiError as e:
+                status[b] = codes[str(e)]
+            except IndexError:
+                status[b] = 5
+            if ns is not None:
+                note_len[b] = len(ns); notes[b, :len(ns)] = ns; meta[b, :len(mt)] = mt
+        out["status_%d" % strict], out["note_len_%d" % strict], out["notes_%d" % strict], out["meta_%d" % strict] = status, note_len, notes, meta
+        print("decode_prepare strict=%d status histogram" % strict, np.bincount(status, minlength=6).tolist())
+    np.savez_compressed(os.path.join(OUT, "decode_prepare.npz"), tokens=tokens, masks=masks, **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_reference_shim()
+    if len(sys.argv) > 1 and sys.argv[1] == "decode":
+        golden_decode_prepare()
+        return
     import torch
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -235,6 +267,7 @@ def main():
     golden_loop("loop_mod_ddpm.npz", "modification", 64, 3, 12, 40, 40, strength=0.75)
     golden_loop("loop_mod_ddim.npz", "modification", 64, 2, 13, 2000, 20, strength=1.0)
     golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
+    golden_decode_prepare()
 
 
 if __name__ == "__main__":

@@ -55,3 +55,28 @@ print("%-42s %8.3f ms  %.1f TFLOP/s fp32" % ("round_argmin", ms, 2.0 * M * V * D
 se = ops.SplitEmbedding(E)
 ms = timeit(lambda: ops.round_argmin_tc(x, se))
 print("%-42s %8.3f ms  %.1f TFLOP/s (4 x 2MVD split-bf16)  %.1f%% of HBM peak on %d algorithmic bytes/token" % ("round_argmin_tc", ms, 8.0 * M * 768 * D / ms / 1e9, 100 * M * 516 / ms / 1e6 / peak, 516))
+
+# ---- batched token-level decode (one warp per row) against the CPU port of the reference's
+# per-row Python (the checker under oracle/, timed on a bounded sample of the same rows)
+import time
+import numpy as np
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import decode_oracle as DO
+from musediffusion_b200.synthetic import make_synthetic_batch
+cond = make_synthetic_batch("modification", B, L, seed=7)
+rows = cond["input_ids"].copy()
+for b in range(B):                      # keep roughly as many BARs as chord bars so that most rows take the full path
+    n0 = int((cond["input_mask"][b] == 0).sum())
+    n_cb = int((rows[b, 11:n0 - 1] == 432).sum())
+    bars = np.nonzero(rows[b, n0:] == 2)[0] + n0
+    rows[b, bars[n_cb:]] = 3
+tok_d = torch.from_numpy(rows).to(dev).to(torch.int32)
+msk_d = torch.from_numpy(cond["input_mask"]).to(dev).to(torch.int32)
+ms = timeit(lambda: ops.decode_prepare(tok_d, msk_d, True))
+st = ops.decode_prepare(tok_d, msk_d, True)[0].cpu().numpy()
+n_cpu = min(B, 32)
+t0 = time.perf_counter()
+want = DO.decode_prepare_batch(rows[:n_cpu], cond["input_mask"][:n_cpu], True)
+cpu_ms = (time.perf_counter() - t0) * 1e3 / n_cpu
+print("%-42s %8.3f ms for %d rows (%.2f us/row; %d OK)   CPU port %.2f ms/row on 1 core   status parity on the sample: %s"
+      % ("decode_prepare strict (L=%d)" % L, ms, B, ms * 1e3 / B, int((st == 0).sum()), cpu_ms, bool((want[0] == st[:n_cpu]).all())))
