@@ -161,6 +161,17 @@ enum {
 int md_decode_prepare(const int32_t* tokens, const int32_t* mask, int B, int L, int strict, int32_t* status,
                       int32_t* note_len, int32_t* notes, int32_t* meta, cudaStream_t stream);
 
+/* ---- modification-mode input preparation, batched -------------------------------------
+ * merge_and_mask (MuseDiffusion/data/preprocess.py:30-58) + helper_filter (:73-81) + collate_batches
+ * (MuseDiffusion/data/wrapper.py:90-126) for a batch of raw (src = meta tokens, trg = event tokens) pairs: every chord
+ * token (195..303) of trg and the token in front of it move behind src; row = [*src', end_token, *trg'] zero padded to
+ * seq_len; mask = 0 over src' + end_token, 1 elsewhere (padding included).  length[b] is the merged length; rows with
+ * length > seq_len (the ones helper_filter drops) are left as pure padding.
+ *   src int32 [B, Ls] + src_len [B], trg int32 [B, Lt] + trg_len [B]  ->  input_ids, input_mask int32 [B, seq_len], length [B] */
+int md_merge_and_mask(const int32_t* src, const int32_t* src_len, const int32_t* trg, const int32_t* trg_len, int B, int Ls,
+                      int Lt, int seq_len, int end_token, int32_t* input_ids, int32_t* input_mask, int32_t* length,
+                      cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

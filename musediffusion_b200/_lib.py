@@ -35,6 +35,7 @@ SIGNATURES = {
     "md_q_sample": [c_p, c_p, c_u64, c_u64, c_i64, c_p, c_i, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p],
     "md_fill_normal": [c_p, c_i64, c_u64, c_u64, c_i64, c_f, c_p],
     "md_decode_prepare": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "md_merge_and_mask": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
 }
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_POS_TIME = 0, 1, 2, 4

@@ -327,3 +327,20 @@ def decode_prepare(tokens, mask, strict=False):
     call("md_decode_prepare", _p(tok), _p(msk), B, L, 1 if strict else 0, _p(status), _p(note_len), _p(notes), _p(meta),
          _stream())
     return status, note_len, notes, meta
+
+
+def merge_and_mask(src, src_len, trg, trg_len, seq_len, end_token=1):
+    """md_merge_and_mask: preprocess.py:30-58 + :73-81 + wrapper.py:90-126 for a padded batch of raw (src, trg) rows.
+    Returns (input_ids [B, seq_len], input_mask [B, seq_len], length [B]), int32; rows with length > seq_len are padding."""
+    B = src_len.shape[0]
+    dev = trg.device
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    src, src_len, trg, trg_len = i32(src), i32(src_len), i32(trg), i32(trg_len)
+    Ls = src.shape[1] if src.dim() == 2 else 0
+    Lt = trg.shape[1]
+    input_ids = torch.empty((B, seq_len), dtype=torch.int32, device=dev)
+    input_mask = torch.empty((B, seq_len), dtype=torch.int32, device=dev)
+    length = torch.empty((B,), dtype=torch.int32, device=dev)
+    call("md_merge_and_mask", _p(src) if Ls else None, _p(src_len), _p(trg), _p(trg_len), B, Ls, Lt, int(seq_len), int(end_token),
+         _p(input_ids), _p(input_mask), _p(length), _stream())
+    return input_ids, input_mask, length

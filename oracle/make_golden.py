@@ -247,11 +247,37 @@ def golden_decode_prepare():
     np.savez_compressed(os.path.join(OUT, "decode_prepare.npz"), tokens=tokens, masks=masks, **out)
 
 
+def golden_merge_and_mask(seq_len=96):
+    """the reference's own helper_tokenize (data/preprocess.py:26-70), helper_filter
+    (:73-81) and collate_batches (data/wrapper.py:90-126) on the rows of preprocess_oracle.merge_cases()."""
+    import torch
+    from MuseDiffusion.data.preprocess import helper_tokenize, helper_filter
+    from MuseDiffusion.data.wrapper import collate_batches
+    from preprocess_oracle import merge_cases
+    src, src_len, trg, trg_len = merge_cases()
+    B = len(src_len)
+    raw = {"src": [src[b, :src_len[b]].tolist() for b in range(B)], "trg": [trg[b, :trg_len[b]].tolist() for b in range(B)]}
+    merged = helper_tokenize(raw, num_proc=1)
+    length = np.array(merged["length"], np.int64)
+    kept = helper_filter(merged, seq_len=seq_len, num_proc=1)
+    assert len(kept) == int((length <= seq_len).sum())
+    rows = [{"input_ids": torch.tensor(kept["input_ids"][i]), "input_mask": torch.tensor(kept["input_mask"][i]),
+             "length": kept["length"][i]} for i in range(len(kept))]
+    col = collate_batches(rows, seq_len=seq_len)
+    np.savez_compressed(os.path.join(OUT, "merge_and_mask.npz"), src=src, src_len=src_len, trg=trg, trg_len=trg_len,
+                        seq_len=seq_len, length=length, kept_input_ids=col["input_ids"].numpy(),
+                        kept_input_mask=col["input_mask"].numpy(), kept_length=col["length"].numpy())
+    print("merge_and_mask.npz", B, "rows,", len(kept), "kept at seq_len", seq_len)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_reference_shim()
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         golden_decode_prepare()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "merge":
+        golden_merge_and_mask()
         return
     import torch
     torch.manual_seed(0)
@@ -268,6 +294,7 @@ def main():
     golden_loop("loop_mod_ddim.npz", "modification", 64, 2, 13, 2000, 20, strength=1.0)
     golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
     golden_decode_prepare()
+    golden_merge_and_mask()
 
 
 if __name__ == "__main__":
