@@ -9,7 +9,7 @@
 //   * each softmax thread owns one row of S (tcgen05.ld 32x32b), keeps the running max / sum in registers, writes
 //     P = exp2(..) as packed bf16 into its own TMEM columns,
 //   * O += P V by tcgen05.mma with A = P from TMEM (TS form), B = V tile (MN-major, 128B swizzle) from shared memory,
-//   * O is rescaled lazily in TMEM only when the row max grew by more than 2^8 (exact after final normalisation).
+//   * O is rescaled lazily in TMEM only when the row max grew by more than 2^32 (exact after final normalisation).
 // One persistent CTA per SM works on TWO 128-row Q tiles of the same (b, h) so the tensor pipe computes S for one
 // tile while the other tile's softmax runs, and both tiles share every K/V stage brought in by TMA.
 //
@@ -45,7 +45,10 @@ constexpr int kAttSmem = 1024 + (4 + 2 * ATT_STAGES + 2) * ATT_TILE_BYTES + 512 
 // warpgroup has READ S(j) into registers — the tensor pipe's latency leaves the softmax critical path.
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_P0 = 256, TM_P1 = 320, TM_O0 = 384, TM_O1 = 448;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kRescaleThreshold = 8.0f;   // log2 units
+// Lazy-rescale threshold in log2 units: P and the running sums may grow to 2^32 times their value under an exact running
+// max before O is rescaled — far inside the bf16 / fp32 exponent range (2^127), and it makes the TMEM round trip of the
+// rescale rare (8, the usual choice for fp16 P, rescaled in ~20 % of the key blocks and cost ~2 %).  MD_ATT_THR overrides.
+constexpr float kRescaleThreshold = 32.0f;
 
 struct AttArgs {
     int B, L, NH;
@@ -54,6 +57,7 @@ struct AttArgs {
     int n_kv;           // ceil(L/128)
     int total_work;     // B * NH * n_pairs
     __nv_bfloat16* out; // [B*L, NH*64]
+    float rescale_thr;  // lazy-rescale threshold in log2 units (see kRescaleThreshold)
     int turn_every;     // 1: the two Q tiles alternate on the exp2 phase every key block; 0: only on block 0 (phase offset)
     long long* trace;   // optional [role 10][event 8][step 64] clock64 stamps of CTA 0 (debug / tuning)
 };
@@ -324,7 +328,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 // lazy rescale decision (the running output lives in TMEM and is only touched after the exponentials,
                 // once P V of block j-1 has retired — the wait is then off the critical path)
                 // (branch-free: block 0 starts from m_used = -inf, so it always "rescales" an empty sum by 2^-inf = 0)
-                const bool need = mb > m_used + kRescaleThreshold;
+                const bool need = mb > m_used + a.rescale_thr;
                 const bool any_resc = __any_sync(0xffffffffu, need) && j > 0;
                 const float f_resc = need ? fast_exp2(m_used - mb) : 1.0f;
                 m_used = need ? mb : m_used;
@@ -508,6 +512,8 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
         }
     }
     a.turn_every = turn_every;
+    static const float thr = getenv("MD_ATT_THR") ? (float)atof(getenv("MD_ATT_THR")) : kRescaleThreshold;
+    a.rescale_thr = thr;
     const int grid = a.total_work < num_sms() ? a.total_work : num_sms();
     kern<<<grid, threads, kAttSmem, stream>>>(tm, tmo, a);
     return check_cuda(cudaGetLastError(), "attention launch");

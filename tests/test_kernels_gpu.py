@@ -94,13 +94,14 @@ def test_attention(B, L, NH):
 
 
 def test_attention_peaky_rows_trigger_rescale():
-    """keys whose score grows along the sequence: the running max rises by > 2^8 between blocks (lazy-rescale path)."""
+    """keys whose score grows along the sequence: the running max rises by far more than the lazy-rescale threshold
+    (2^32) from block to block, so the O / l rescale in TMEM runs repeatedly."""
     B, L, NH = 1, 640, 1
     g = torch.Generator(device="cpu").manual_seed(9)
     q = torch.randn(L, 64, generator=g)
     k = torch.randn(L, 64, generator=g) * 0.1
     k += (torch.arange(L)[:, None] / L) * q.mean(0, keepdim=True).sign() * 0.0
-    k[:, 0] += torch.linspace(0, 6, L)          # later keys score much higher for rows with q[:,0] > 0
+    k[:, 0] += torch.linspace(0, 40, L)         # later keys score much higher for rows with q[:,0] > 0
     q[:, 0] = q[:, 0].abs() * 3
     v = torch.randn(L, 64, generator=g)
     qkv = torch.cat([q, k, v], dim=1).to(torch.bfloat16).to(DEV)
