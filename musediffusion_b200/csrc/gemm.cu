@@ -31,6 +31,7 @@ struct GemmArgs {
     int temb_stride;
     void* out;                     // bf16 or fp32 [M, N]
     int debug_skip;                // tuning experiments only: 1 = no TMA store, 2 = no slab write + no store
+    int idle_wait;                 // bit 0: producer, bit 1: epilogue, bit 2: MMA warp wait with the try_wait suspend hint
 };
 
 template <int BN, bool kCta2 = false>
@@ -117,7 +118,7 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (p.idle_wait & 1) mbar_wait_idle(&empty_bar[stage], phase ^ 1); else mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (kCta2) {
                     // both CTAs credit the LEADER's full barrier: 2 arrivals + the bytes of all four boxes
                     if (is_leader) mbar_arrive_expect_tx_w(&full_bar[stage], 2 * Cfg::kStageBytes);
@@ -141,11 +142,11 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         uint32_t acc_phase = 0;
         if (is_leader) {        // in a pair only the leader CTA issues; its MMAs drive both tensor cores
             for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                if (p.idle_wait & 4) mbar_wait_idle(&tempty_bar[acc], acc_phase ^ 1); else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if (p.idle_wait & 4) mbar_wait_idle(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
                     const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
@@ -181,7 +182,7 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         for (int tile = cta_id; tile < num_tiles; tile += n_cta) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int n0 = n_blk * BN;
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            if (p.idle_wait & 2) mbar_wait_idle(&tfull_bar[acc], acc_phase); else mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = m_blk * BMT + (int)cta_rank * BM + q * 32;
             const int row = row0 + lane;
@@ -458,6 +459,9 @@ extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void*
     a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
     a.bias = bias; a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
     { const char* e = getenv("MD_GEMM_DEBUG_SKIP"); a.debug_skip = e ? atoi(e) : 0; }
+    // sleeping waits (try_wait suspend hint) for the warps that wait long: the TMA producer always, the epilogue warps when the
+    // mainloop is long (K >= 2048: FFN2 +2..5 %); the epilogue-bound K = 768 shapes keep the polling wait (measured -1 % asleep)
+    { const char* e = getenv("MD_GEMM_IDLE"); a.idle_wait = e ? atoi(e) : (K >= 2048 ? 3 : 1); }
     if (pair) return dispatch_epi_pair<false>(epilogue, tmA, tmB, tmC, a, stream);
     if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, tmC, a, stream)
                                      : dispatch_epi<256, false>(epilogue, tmA, tmB, tmC, a, stream);
