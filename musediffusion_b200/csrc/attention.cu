@@ -282,7 +282,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             // One mbarrier wait per key block: S(j+1)'s commit also covers P V(j-1) (tcgen05.commit tracks every earlier
             // MMA of the issuing thread), so waiting for it after the exponentials of block j both frees P / O for
             // rewriting and pre-pays the wait at the top of block j+1.
-            mbar_wait(&s_full[x], scnt & 1);
+            mbar_wait_idle(&s_full[x], scnt & 1);      // long at a work-item boundary (a whole item for a phantom tile's warps): sleep
             tc_fence_after();
             for (int j = 0; j < a.n_kv; ++j, ++scnt) {
                 const bool tr = (half == 0);
@@ -407,7 +407,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 else asm volatile("bar.sync 5, %0;" ::"n"(kTileThreads) : "memory");
                 l_sum += sm[(half ^ 1) * 128 + r];
             }
-            mbar_wait(&o_full[x], ocnt & 1);
+            mbar_wait_idle(&o_full[x], ocnt & 1);
             ++ocnt;
             tc_fence_after();
             uint32_t o[OC / 32][32];
