@@ -172,6 +172,20 @@ int md_merge_and_mask(const int32_t* src, const int32_t* src_len, const int32_t*
                       int Lt, int seq_len, int end_token, int32_t* input_ids, int32_t* input_mask, int32_t* length,
                       cudaStream_t stream);
 
+/* ---- sample-quality metrics on decoded note sequences, batched ------------------------
+ * md_sequence_metrics: per sequence the rhythm [32] / melody [12] / harmony [12] vectors of get_vectors
+ * (MuseDiffusion/metric.py:4-75; status 1 + zero vectors where the reference raises) and the token counts behind
+ * Controllability_Pitch / Controllability_Velocity (:131-169).
+ *   notes int32 [B, Ln] + note_len [B] (md_decode_prepare's outputs), meta int32 [B, 11]
+ *   vectors f32 [B, 56] = rhythm | melody | harmony;  status int32 [B];
+ *   stats int32 [B, 4] = sum and count of pitch tokens (3..130), count of velocity tokens (131..194), velocity tokens
+ *   outside [meta[7] - 524, meta[8] - 524] (with the reference's 130 / 195 "unbounded" sentinels)
+ * md_onnc: MSIM = product of the three Gram matrices with a zero diagonal and its row arg-max (ONNC, :89-109);
+ *   vectors f32 [N, 56] -> msim f32 [N, N] (may be NULL), most_sim int32 [N]. */
+int md_sequence_metrics(const int32_t* notes, const int32_t* note_len, const int32_t* meta, int B, int Ln, float* vectors,
+                        int32_t* status, int32_t* stats, cudaStream_t stream);
+int md_onnc(const float* vectors, int N, float* msim, int32_t* most_sim, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,8 @@ SIGNATURES = {
     "md_fill_normal": [c_p, c_i64, c_u64, c_u64, c_i64, c_f, c_p],
     "md_decode_prepare": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "md_merge_and_mask": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
+    "md_sequence_metrics": [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+    "md_onnc": [c_p, c_i, c_p, c_p, c_p],
 }
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_POS_TIME = 0, 1, 2, 4

@@ -344,3 +344,27 @@ def merge_and_mask(src, src_len, trg, trg_len, seq_len, end_token=1):
     call("md_merge_and_mask", _p(src) if Ls else None, _p(src_len), _p(trg), _p(trg_len), B, Ls, Lt, int(seq_len), int(end_token),
          _p(input_ids), _p(input_mask), _p(length), _stream())
     return input_ids, input_mask, length
+
+
+def sequence_metrics(notes, note_len, meta):
+    """md_sequence_metrics (metric.py:4-75, 131-169): notes [B, Ln], note_len [B], meta [B, 11] integer CUDA tensors ->
+    (vectors f32 [B, 56] = rhythm | melody | harmony, status int32 [B], stats int32 [B, 4])."""
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    notes, note_len, meta = i32(notes), i32(note_len), i32(meta)
+    B, Ln = notes.shape
+    dev = notes.device
+    vectors = torch.empty((B, 56), dtype=torch.float32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    call("md_sequence_metrics", _p(notes), _p(note_len), _p(meta), B, Ln, _p(vectors), _p(status), _p(stats), _stream())
+    return vectors, status, stats
+
+
+def onnc_nearest(vectors, want_msim=False):
+    """md_onnc (metric.py:99-107): vectors f32 [N, 56] -> (most_sim int32 [N], msim f32 [N, N] or None)."""
+    vectors = vectors.to(torch.float32).contiguous()
+    N = vectors.shape[0]
+    most = torch.empty((N,), dtype=torch.int32, device=vectors.device)
+    msim = torch.empty((N, N), dtype=torch.float32, device=vectors.device) if want_msim else None
+    call("md_onnc", _p(vectors), N, _p(msim), _p(most), _stream())
+    return most, msim

@@ -270,9 +270,33 @@ def golden_merge_and_mask(seq_len=96):
     print("merge_and_mask.npz", B, "rows,", len(kept), "kept at seq_len", seq_len)
 
 
+def golden_metrics():
+    """the reference's own metric.py (get_vectors, ONNC, Controllability_*) on the
+    sequences of metric_oracle.metric_cases()."""
+    import torch
+    from MuseDiffusion.metric import get_vectors, ONNC, Controllability_Pitch, Controllability_Velocity
+    from metric_oracle import metric_cases
+    metas, midis, lens = metric_cases()
+    rows = [midis[b, :lens[b]] for b in range(len(lens))]
+    vecs = [get_vectors(r) for r in rows]
+    rhythm = torch.stack([v[0] for v in vecs]).numpy()
+    melody = torch.stack([v[1] for v in vecs]).numpy()
+    harmony = torch.stack([v[2] for v in vecs]).numpy()
+    score, msim, most = ONNC(rows, return_MSIM=True, return_mostsim=True)
+    cp = Controllability_Pitch(metas, rows)
+    cv = Controllability_Velocity(metas, rows)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), metas=metas, midis=midis, lens=lens, rhythm=rhythm, melody=melody,
+                        harmony=harmony, onnc=float(score), msim=msim.numpy(), most_sim=most.numpy(),
+                        cp=np.array(cp, np.int64), cv=np.array(cv, np.int64))
+    print("metrics.npz", len(rows), "rows, ONNC %.4f CP %s CV %s" % (float(score), cp, cv))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_reference_shim()
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        golden_metrics()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         golden_decode_prepare()
         return
@@ -295,6 +319,7 @@ def main():
     golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
     golden_decode_prepare()
     golden_merge_and_mask()
+    golden_metrics()
 
 
 if __name__ == "__main__":
