@@ -210,15 +210,17 @@ _split_cache = {}
 
 
 def split_embedding(E):
-    """cached SplitEmbedding for a weight tensor (keyed by storage + version, a handful of entries at most)."""
+    """cached SplitEmbedding for a weight tensor, keyed by storage address + version.  The entry keeps a reference to the
+    tensor it was built from: while it is cached its memory cannot be freed and handed to another embedding table, so an
+    equal key always means the same contents (a freed table's address IS reused by the caching allocator)."""
     key = (E.data_ptr(), E._version, tuple(E.shape), str(E.device))
-    se = _split_cache.get(key)
-    if se is None:
+    hit = _split_cache.get(key)
+    if hit is None:
         if len(_split_cache) > 8:
             _split_cache.clear()
-        se = SplitEmbedding(E)
-        _split_cache[key] = se
-    return se
+        hit = (SplitEmbedding(E), E)
+        _split_cache[key] = hit
+    return hit[0]
 
 
 def round_argmin_tc(x, se, cst=None, mode=0, want_margin=False, out=None):

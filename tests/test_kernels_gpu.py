@@ -133,6 +133,21 @@ def test_attention_many_work_items_deterministic():
     assert worst < 1.5e-2, worst
 
 
+def test_split_embedding_cache_survives_address_reuse():
+    """A freed embedding table's address is handed to the next table of the same shape by the caching allocator: the
+    cached split must never be served for different contents (regression: stale split -> every free token rounded
+    against another model's embeddings)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(500, 128, generator=g).to(DEV)
+    for k in range(6):
+        E = (torch.randn(729, 128, generator=g) * (1 + k)).to(DEV)
+        want = ops.round_argmin(x, E)
+        got = ops.round_argmin_tc(x, ops.split_embedding(E))
+        assert torch.equal(got, want), k
+        del E
+        torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------------------------------ layernorm etc.
 @pytest.mark.parametrize("M,H", [(1, 768), (333, 768), (4192, 768), (100, 1024), (7, 256)])
 def test_layernorm(M, H):
