@@ -65,23 +65,23 @@ def _c(t, dtype=None):
 TABLE_ORDER = ["posterior_mean_coef1", "posterior_mean_coef2", "model_log_variance", "sqrt_recip_alphas_cumprod",
                "sqrt_recipm1_alphas_cumprod", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
                "sqrt_one_minus_alphas_cumprod"]
-_current_schedule_key = [None]
+_current_schedule_key = {}      # CUDA device index -> key of the schedule resident in that device's tables
 
 
 def current_schedule_key():
-    return _current_schedule_key[0]
+    return _current_schedule_key.get(torch.cuda.current_device())
 
 
 def set_schedule(tables64, key=None):
     """tables64: dict name -> float64 numpy [T].  Cast to fp32 exactly like _extract_into_tensor
     (MuseDiffusion/models/diffusion.py:914) and uploaded once; `key` lets callers skip redundant uploads."""
-    if key is not None and _current_schedule_key[0] is key:
+    if key is not None and current_schedule_key() is key:
         return
     T = len(tables64[TABLE_ORDER[0]])
     host = np.ascontiguousarray(np.stack([np.asarray(tables64[n], dtype=np.float64).astype(np.float32)
                                           for n in TABLE_ORDER]))
     call("md_set_schedule", host.ctypes.data, T, _stream())
-    _current_schedule_key[0] = key
+    _current_schedule_key[torch.cuda.current_device()] = key
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
