@@ -176,6 +176,7 @@ class TransformerNetModel(nn.Module):
                                               nn.Linear(cfg.hidden_size, output_dims))
         self._pack = None
         self._pack_key = None
+        self._pack_refs = None
         self._ws = {}
 
     # ------------------------------------------------------------------------------------------ packing
@@ -187,6 +188,10 @@ class TransformerNetModel(nn.Module):
         if force or self._pack is None or key != self._pack_key:
             self._pack = WeightPack(self)
             self._pack_key = key
+            # keep the storages the key was taken from alive for as long as the pack is: `.to()` / `load_state_dict` on
+            # another device replace them, and the caching allocator hands a freed block to the next tensor of the same
+            # size — an equal (address, version) key must always mean the same weights
+            self._pack_refs = [p.data for p in self.parameters()]
             self._ws = {}
         return self._pack
 
