@@ -311,11 +311,11 @@ def summarize_profile(prof, B):
 
 
 def cpu_baseline_sample():
-    """bounded CPU sample of the same workload with the oracle port: 1 sequence x 2 chain steps (~15-25 s)."""
+    """bounded CPU sample of the same workload with the oracle port: 1 sequence x 5 chain steps (~10-15 s on 16 cores)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import musediff_oracle as O
-    Bc, steps = 1, 2
+    Bc, steps = 1, 5
     p = O.make_random_params(seed=0, seq_len=L)
     s = O.make_schedule("sqrt", DIFFUSION_STEPS)
     cond = O.make_synthetic_batch("modification", Bc, L, seed=105)
