@@ -1,4 +1,4 @@
-"""Tensor-level wrappers over the C-ABI kernels, plus their registration as `torch.ops.musediff_b200.*` custom ops.
+"""Tensor-level wrappers over the C-ABI kernels (ctypes; one wrapper per `md_*` entry of include/musediff_b200.h).
 
 Every function here launches hand-written sm_100a kernels on the current CUDA stream; inputs must be CUDA tensors
 (a CPU tensor raises — there is no fallback)."""
