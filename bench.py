@@ -3,7 +3,9 @@
 reverse-diffusion sampling; ms per denoiser step).
 
   python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
-  python bench.py --impl reference --steps K --warmup W    the reference algorithm's CPU port (numpy oracle) on host cores
+  python bench.py --impl reference --steps K --warmup W    the UNMODIFIED reference's CPU path (oracle/_ref via oracle/ref_harness.py)
+                                                            on the host cores; the numpy port if that tree is absent
+  python bench.py --mode generation --batch 128            BASELINE.json configs[2] (unconditional generation path)
 
 Workload (config 2 of BASELINE.json): base TransformerNetModel (bert-base encoder, seq_len 2096, hidden_dim 128,
 vocab 729), random-init weights, synthetic ComMU-shaped modification batch, 256 sequences per GPU, DDPM chain of
@@ -90,58 +92,94 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference algorithm on the host CPU: the numpy port under oracle/ (the reference itself is Python and does
-    not travel to the GPU box).  Each step = one reverse step of the same chain on a bounded
-    sample of the workload (args.ref_batch sequences of the same shape)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _reference_sampler():
+    """The UNMODIFIED reference (oracle/_ref copy on the GPU box, /root/reference in the build container) on the host CPU,
+    or None when neither tree is present (then the numpy port of oracle/ is the CPU arm)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_harness
+        if not ref_harness.available():
+            return None
+        return ref_harness.ReferenceSampler(seq_len=L, diffusion_steps=DIFFUSION_STEPS, seed=0)
+    except Exception as exc:                                    # noqa: BLE001 - fall back to the port, but say why
+        print("bench: reference import failed (%s: %s); using the numpy port" % (type(exc).__name__, exc), file=sys.stderr)
+        return None
+
+
+def time_reference_cpu(mode, B, warmup, steps):
+    """the reference's own `sample_fn(...)` + `get_logits` + `argmax` (run/sample.py:200-220), fp32,
+    all host threads, on B synthetic sequences of the workload; the chain is cut to `steps` reverse steps through the
+    reference's own t_enc argument (every step of the chain costs the same) and extrapolated to 2000.
+    Returns (seconds per reverse step, kind, threads, description)."""
     import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import musediff_oracle as O
-    B = args.ref_batch
+    cond = O.make_synthetic_batch(mode, B, L, seed=105)
+    ref = _reference_sampler() if (L, H, F, NL, NH) == (2096, 768, 3072, 12, 12) else None
+    if ref is not None:
+        import torch
+        tcond = {k: torch.from_numpy(np.asarray(v)) for k, v in cond.items()}
+        torch.manual_seed(105)
+        if warmup > 0:
+            ref.sample(tcond, mode, DIFFUSION_STEPS, strength=1.0, top_p=1, n_steps=warmup)
+        tic = time.perf_counter()
+        ref.sample(tcond, mode, DIFFUSION_STEPS, strength=1.0, top_p=1, n_steps=steps)
+        per_step = (time.perf_counter() - tic) / steps
+        return per_step, "reference", ref.threads, (
+            "unmodified MuseDiffusion p_sample_loop + denoised_fn_round + get_logits/argmax (run/sample.py:177-220) via "
+            "oracle/ref_harness.py, fp32 torch CPU, %d threads: %d sequences x %d chain steps (t_enc), %.2f s/step, "
+            "extrapolated to the 2000-step chain" % (ref.threads, B, steps, per_step))
     p = O.make_random_params(seed=0, seq_len=L)
     s = O.make_schedule("sqrt", DIFFUSION_STEPS)
-    cond = O.make_synthetic_batch("modification", B, L, seed=105)
     x_start = O.get_embeds(p, cond["input_ids"])
     mask = np.broadcast_to(cond["input_mask"][..., None], x_start.shape)
     noise = O.NoiseStream(105)
     x = O.q_sample(s, x_start, np.full((B,), DIFFUSION_STEPS - 1), noise.randn(x_start.shape), mask)
     E = p["word_embedding.weight"]
     times = []
-    for k in range(args.warmup + args.steps):
-        i = DIFFUSION_STEPS - 1 - k
-        t = np.full((B,), i, dtype=np.int64)
+    for k in range(warmup + steps):
+        t = np.full((B,), DIFFUSION_STEPS - 1 - k, dtype=np.int64)
         tic = time.perf_counter()
         mo = O.denoiser_forward(p, x, s.model_timestep(t))
         x = O.p_sample_step(s, x, t, mo, noise.truncated(x.shape, 1), E, True, mask, x_start)["sample"]
         times.append(time.perf_counter() - tic)
-    tic = time.perf_counter()
-    O.logits_argmax(p, x)
-    t_dec = time.perf_counter() - tic
-    ms = 1e3 * sum(times[args.warmup:]) / args.steps
-    value = B / (ms * 1e-3 * DIFFUSION_STEPS + t_dec)
-    cores = os.cpu_count()
+    per_step = sum(times[warmup:]) / steps
+    return per_step, "port", os.cpu_count(), (
+        "numpy port of the reference algorithm (oracle/musediff_oracle.py; reference tree not present): %d sequences x %d "
+        "chain steps, %.2f s/step, extrapolated to the 2000-step chain" % (B, steps, per_step))
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, on our arm's config /
+    metric / unit; each step = one reverse step of the chain on a bounded sample (args.ref_batch sequences, BASELINE.md
+    section 3 uses 4).  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    per_step, kind, threads, sample = time_reference_cpu(args.mode, B, args.warmup, args.steps)
+    ms = 1e3 * per_step
+    value = B / (per_step * DIFFUSION_STEPS)
     line = {"impl": "reference", "metric": "sequences/sec full reverse-diffusion sampling", "value": value,
             "unit": "sequences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(B, 1, note="CPU port of the reference algorithm (numpy, host BLAS threads)"),
-            "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": "port",
-                             "sample": "%d sequences x %d consecutive chain steps of the same workload, fp32 numpy "
-                                       "(oracle/musediff_oracle.py), extrapolated to the 2000-step chain" % (B, args.steps)},
+            "config": workload_config(args.batch, args.gpus, mode=args.mode),
+            "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(batch_per_gpu, n_gpus, note=None):
+def workload_config(batch_per_gpu, n_gpus, note=None, mode="modification"):
     base = (L, H, F, NL, NH) == (2096, 768, 3072, 12, 12)
-    c = {"workload": ("BASELINE.json configs[1]: base TransformerNetModel (bert-base encoder 12x768, seq_len 2096, "
-                      "hidden_dim 128, vocab 729)" if base else
+    which = ("configs[1]" if mode == "modification" else "configs[2]") if base else "configs[4] family"
+    c = {"workload": ("BASELINE.json %s: base TransformerNetModel (bert-base encoder 12x768, seq_len 2096, "
+                      "hidden_dim 128, vocab 729)" % which if base else
                       "BASELINE.json configs[4] family: scaled denoiser (encoder %dx%d, %d heads, FFN %d, seq_len %d, "
                       "hidden_dim 128, vocab 729)" % (NL, H, NH, F, L)) +
-                     " random-init; modification (seq2seq) sampling, DDPM 2000 steps, "
-                     "rounding every step, top_p=1; batch %d sequences per GPU" % batch_per_gpu,
+                     " random-init; %s sampling, DDPM 2000 steps, "
+                     "rounding every step, top_p=1; batch %d sequences per GPU"
+                     % ("modification (seq2seq)" if mode == "modification" else "unconditional generation (sample_generation path)",
+                        batch_per_gpu),
          "global_batch": batch_per_gpu * n_gpus, "seq_len": L, "chain_steps": DIFFUSION_STEPS,
          "parallelism": "dp%d (batch sharded by sequence, replicated weights, no collective in the loop)" % n_gpus,
          "step_definition": "one reverse-diffusion step over the whole batch; value extrapolated to the full chain",
@@ -177,7 +215,7 @@ def run_ours(args):
     model_emb = build_model_emb(model, dev)
     seed_all(105, deterministic=True)
     diffusion.seq_offset = rank * B
-    cond_np = make_synthetic_batch("modification", B, L, seed=105 + rank)
+    cond_np = make_synthetic_batch(args.mode, B, L, seed=105 + rank)
     cond_host = {k: torch.from_numpy(v).pin_memory() for k, v in cond_np.items() if k != "length"}
     fn = partial(denoised_fn_round, model_emb, dist=None)
 
@@ -186,8 +224,13 @@ def run_ours(args):
     mask_ori = cond_host["input_mask"].to(dev)
     x_start = model.get_embeds(ids)
     mask = torch.broadcast_to(mask_ori.unsqueeze(-1), x_start.shape)
-    x_noised = diffusion.q_sample(x_start.unsqueeze(-1), torch.full((B, 1), DIFFUSION_STEPS - 1, device=dev),
-                                  mask=mask).squeeze(-1)
+    if args.mode == "generation":                              # run/sample.py:190-193
+        x_noised = ops.q_sample(x_start, None, seed=diffusion._seed(), step_counter=diffusion._next_counter(),
+                                seq_offset=diffusion.seq_offset, mask=mask_ori)
+    else:                                                      # run/sample.py:195-197
+        x_noised = diffusion.q_sample(x_start.unsqueeze(-1), torch.full((B, 1), DIFFUSION_STEPS - 1, device=dev),
+                                      mask=mask).squeeze(-1)
+    model.decode_tokens(x_noised)                              # one-time set-up of the decode kernel (split embedding, attributes)
     n_total = DIFFUSION_STEPS if args.full_chain else args.warmup + args.steps
     gen = diffusion._loop(_lib.STEP_DDPM, model, tuple(x_start.shape), x_noised, True, fn, None, dev, False, 1, 0, True,
                           mask, x_start, 0.0, list(range(DIFFUSION_STEPS))[::-1][:n_total + 1], want_aux=False)
@@ -247,9 +290,13 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
             tic = time.perf_counter()
-            tok = sample_batch(model, diffusion, model_emb, cond_host, "modification", DIFFUSION_STEPS, DIFFUSION_STEPS,
-                               strength=strength, top_p=1, clamp_step=0, device=dev)
-            tok_host = tok.to("cpu", non_blocking=False)
+            if args.mode == "generation":
+                tok = sample_generation_steps(model, diffusion, model_emb, cond_host, k_e2e, dev)
+            else:
+                tok = sample_batch(model, diffusion, model_emb, cond_host, "modification", DIFFUSION_STEPS, DIFFUSION_STEPS,
+                                   strength=strength, top_p=1, clamp_step=0, device=dev)
+            tok = dist.all_gather_tokens(tok)                      # NCCL all-gather of the decoded ids (no-op at N = 1)
+            tok_host = tok.to("cpu", non_blocking=False) if rank == 0 else None
             torch.cuda.synchronize()
             t_e2e = time.perf_counter() - tic
         te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
@@ -258,25 +305,46 @@ def run_ours(args):
         t_e2e = float(te[0])
         e2e = {"value": (B * world) / (t_e2e * DIFFUSION_STEPS / k_e2e), "unit": "sequences/s",
                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in cond_host.values())),
-               "d2h_bytes_per_step": int(tok_host.numel() * tok_host.element_size()),
+               "d2h_bytes_per_step": int(B * world * L * 8),
+               "gathered": "decoded ids of all ranks all-gathered over NCCL inside the timed region, rank 0 copies [%d, %d] int64 to the host" % (B * world, L),
                "note": "sample_batch() public API, %d chain steps via t_enc incl. H2D ids/mask, embedding gather, "
                        "q_sample, decode and D2H tokens; whole call scaled by 2000/%d" % (k_e2e, k_e2e),
                "seconds_per_call": t_e2e}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_sample()
+        cpu_baseline = cpu_baseline_sample(args.mode)
 
     if rank == 0:
         line = {"metric": "sequences/sec full reverse-diffusion sampling", "value": value, "unit": "sequences/s",
                 "n_gpus": world, "steps": timed_steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B, world), "ms_per_denoiser_step": ms_step, "ms_decode": ms_decode,
+                "config": workload_config(B, world, mode=args.mode), "ms_per_denoiser_step": ms_step, "ms_decode": ms_decode,
                 "step_tflops": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
                 "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "kernels": breakdown}
         print(json.dumps(line))
     dist.barrier()
+
+
+def sample_generation_steps(model, diffusion, model_emb, cond, k_steps, dev):
+    """sample_batch()'s generation branch (run/sample.py:177-220) cut to the first k_steps chain indices through the
+    reference's own t_enc argument (generation mode has no strength flag to shorten the chain with)."""
+    import torch
+    from functools import partial
+    from musediffusion_b200 import ops
+    from musediffusion_b200.rounding import denoised_fn_round
+    ids = torch.as_tensor(cond["input_ids"]).to(dev, non_blocking=True)
+    mask_ori = torch.as_tensor(cond["input_mask"]).to(dev, non_blocking=True)
+    x_start = model.get_embeds(ids)
+    mask = torch.broadcast_to(mask_ori.unsqueeze(-1), x_start.shape)
+    x_noised = ops.q_sample(x_start, None, seed=diffusion._seed(), step_counter=diffusion._next_counter(),
+                            seq_offset=diffusion.seq_offset, mask=mask_ori)
+    samples = diffusion.p_sample_loop(model=model, shape=tuple(x_start.shape), noise=x_noised, clip_denoised=True,
+                                      denoised_fn=partial(denoised_fn_round, model_emb, dist=None), model_kwargs=cond,
+                                      top_p=1, clamp_step=0, clamp_first=True, mask=mask, x_start=x_start, gap=1,
+                                      t_enc=k_steps, only_last=True)
+    return model.decode_tokens(samples[-1])
 
 
 def ncu_traffic(kernel, B):
@@ -310,28 +378,13 @@ def summarize_profile(prof, B):
     return out
 
 
-def cpu_baseline_sample():
-    """bounded CPU sample of the same workload with the oracle port: 1 sequence x 5 chain steps (~10-15 s on 16 cores)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import musediff_oracle as O
-    Bc, steps = 1, 5
-    p = O.make_random_params(seed=0, seq_len=L)
-    s = O.make_schedule("sqrt", DIFFUSION_STEPS)
-    cond = O.make_synthetic_batch("modification", Bc, L, seed=105)
-    x_start = O.get_embeds(p, cond["input_ids"])
-    mask = np.broadcast_to(cond["input_mask"][..., None], x_start.shape)
-    noise = O.NoiseStream(105)
-    x = O.q_sample(s, x_start, np.full((Bc,), DIFFUSION_STEPS - 1), noise.randn(x_start.shape), mask)
-    tic = time.perf_counter()
-    for k in range(steps):
-        t = np.full((Bc,), DIFFUSION_STEPS - 1 - k, dtype=np.int64)
-        mo = O.denoiser_forward(p, x, s.model_timestep(t))
-        x = O.p_sample_step(s, x, t, mo, noise.truncated(x.shape, 1), p["word_embedding.weight"], True, mask, x_start)["sample"]
-    per_step = (time.perf_counter() - tic) / steps
-    return {"value": Bc / (per_step * DIFFUSION_STEPS), "unit": "sequences/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d sequence x %d consecutive chain steps (fp32 numpy oracle, %.2f s/step), extrapolated to 2000 steps"
-                      % (Bc, steps, per_step)}
+def cpu_baseline_sample(mode):
+    """bounded CPU sample of the same workload (10-30 s of host work): the unmodified reference at batch 4 (BASELINE.md
+    section 3) for 1 warm-up + 3 timed chain steps; the numpy port (1 sequence) if the reference tree is absent."""
+    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "MuseDiffusion")) or os.path.isdir("/root/reference/MuseDiffusion")
+    Bc = 4 if have_ref else 1
+    per_step, kind, threads, sample = time_reference_cpu(mode, Bc, 1, 3)
+    return {"value": Bc / (per_step * DIFFUSION_STEPS), "unit": "sequences/s", "cores": threads, "kind": kind, "sample": sample}
 
 
 def main():
@@ -341,7 +394,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
-    ap.add_argument("--ref-batch", type=int, default=1, help="sequences per step for --impl reference")
+    ap.add_argument("--ref-batch", type=int, default=4, help="sequences per step for --impl reference (BASELINE.md section 3: 4)")
+    ap.add_argument("--mode", default="modification", choices=["modification", "generation"],
+                    help="modification = BASELINE.json configs[1] (default); generation = configs[2] (sample_generation path)")
     ap.add_argument("--full-chain", action="store_true", help="run all 2000 chain steps instead of extrapolating")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")

@@ -475,8 +475,8 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
     a.n_kv = (L + ATT_BKV - 1) / ATT_BKV;
     a.total_work = B * NH * a.n_pairs;
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
-    a.trace = nullptr;
-    if (const char* tp = getenv("MD_ATT_TRACE_PTR")) a.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
+    static long long* const trace_ptr = getenv("MD_ATT_TRACE_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("MD_ATT_TRACE_PTR"), nullptr, 0)) : nullptr;
+    a.trace = trace_ptr;     // tools/att_trace.py sets it before the first call; read once
     CUtensorMap tmo;
     if (int e = make_tmap_bf16_3d(&tmo, out, H, L, B, H, (uint64_t)L * H, 64, 128)) return e;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const AttArgs);
@@ -500,17 +500,14 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
         if (split == 2) kern = turns ? MD_ATT_PICK(true, 2) : MD_ATT_PICK(false, 2);
         else kern = turns ? MD_ATT_PICK(true, 1) : MD_ATT_PICK(false, 1);
 #undef MD_ATT_PICK
-        if (getenv("MD_ATT_TRACE_PTR")) {      // timeline tracing build of the selected split (tools/att_trace.py)
+        if (trace_ptr != nullptr) {      // timeline tracing build of the selected split (tools/att_trace.py)
             if (split == 2) kern = turns ? attention_kernel<true, 0, 2, true> : attention_kernel<false, 0, 2, true>;
             else kern = turns ? attention_kernel<true, 2, 1, true> : attention_kernel<false, 2, 1, true>;
         }
         threads = split == 2 ? AttCfg<2>::kThreads : AttCfg<1>::kThreads;
-        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem),
-                       "cudaFuncSetAttribute(attention)")) {
-            kern = nullptr;
-            return MD_ERR_CUDA;
-        }
     }
+    static bool attr_set[kMaxDevices] = {false};
+    if (ensure_dyn_smem(kern, kAttSmem, attr_set, "cudaFuncSetAttribute(attention)")) return MD_ERR_CUDA;
     a.turn_every = turn_every;
     static const float thr = getenv("MD_ATT_THR") ? (float)atof(getenv("MD_ATT_THR")) : kRescaleThreshold;
     a.rescale_thr = thr;

@@ -19,6 +19,26 @@ void set_last_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 
 // ----------------------------------------------------------------------------------------------
+// per-device host state.  A process may drive several GPUs (one cudaSetDevice per thread / per call): everything the
+// library remembers between calls — SM count, "dynamic shared memory attribute already raised" flags, the schedule
+// tables — is indexed by the calling thread's current device, never process-global.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+int current_device();      // cudaGetDevice(), clamped to [0, kMaxDevices)
+int num_sms();             // multiprocessor count of the current device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); `done` = that kernel's static flag array
+template <typename Kernel>
+inline int ensure_dyn_smem(Kernel kern, int bytes, bool (&done)[kMaxDevices], const char* what) {
+    const int dev = current_device();
+    if (done[dev]) return 0;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what)) return -2;
+    done[dev] = true;
+    return 0;
+}
+// environment tuning switches are read ONCE per process (never per call)
+int env_int(const char* name, int dflt);
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 MD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -33,9 +33,14 @@ int num_sms();
 enum { TAB_C1 = 0, TAB_C2, TAB_LOGVAR, TAB_SR, TAB_SRM1, TAB_AB, TAB_ABP, TAB_SQRT_AB, TAB_SQRT_1MAB, TAB_COUNT };
 constexpr int kConstTabs = 7;
 __constant__ float c_sched[kConstTabs * MD_MAX_CONST_T];
-static float* g_sched_dev = nullptr;   // [TAB_COUNT][T] device copy (q_sample tables, and T > MD_MAX_CONST_T)
-static int g_sched_T = 0;
-static int g_sched_cap = 0;
+// one table set per device (a process may drive several GPUs; __constant__ memory is per device already)
+struct SchedState {
+    float* dev = nullptr;   // [TAB_COUNT][T] device copy (q_sample tables, and T > MD_MAX_CONST_T)
+    int T = 0;
+    int cap = 0;
+};
+static SchedState g_sched[kMaxDevices];
+static SchedState& sched_state() { return g_sched[current_device()]; }
 
 struct SchedRef {
     const float* dev;  // device table or nullptr -> constant memory
@@ -45,9 +50,10 @@ struct SchedRef {
     }
 };
 static SchedRef sched_ref() {
+    const SchedState& st = sched_state();
     SchedRef s;
-    s.T = g_sched_T;
-    s.dev = (g_sched_T <= MD_MAX_CONST_T) ? nullptr : g_sched_dev;
+    s.T = st.T;
+    s.dev = (st.T <= MD_MAX_CONST_T) ? nullptr : st.dev;
     return s;
 }
 
@@ -645,14 +651,16 @@ extern "C" __attribute__((visibility("default"))) int md_abi_version(void) { ret
 
 extern "C" __attribute__((visibility("default"))) int md_set_schedule(const float* tables, int T, cudaStream_t stream) {
     if (tables == nullptr || T <= 0) { set_last_error("md_set_schedule: bad arguments (T=%d)", T); return MD_ERR_ARG; }
-    if (T > g_sched_cap) {
-        if (g_sched_dev) cudaFree(g_sched_dev);
-        g_sched_dev = nullptr;
-        if (check_cuda(cudaMalloc(&g_sched_dev, sizeof(float) * TAB_COUNT * T), "cudaMalloc(schedule)")) return MD_ERR_CUDA;
-        g_sched_cap = T;
+    SchedState& st = sched_state();          // the calling thread's current device
+    if (T > st.cap) {
+        if (st.dev) cudaFree(st.dev);
+        st.dev = nullptr;
+        st.cap = 0;
+        if (check_cuda(cudaMalloc(&st.dev, sizeof(float) * TAB_COUNT * T), "cudaMalloc(schedule)")) return MD_ERR_CUDA;
+        st.cap = T;
     }
-    g_sched_T = T;
-    if (check_cuda(cudaMemcpyAsync(g_sched_dev, tables, sizeof(float) * TAB_COUNT * T, cudaMemcpyHostToDevice, stream),
+    st.T = T;
+    if (check_cuda(cudaMemcpyAsync(st.dev, tables, sizeof(float) * TAB_COUNT * T, cudaMemcpyHostToDevice, stream),
                    "cudaMemcpyAsync(schedule)"))
         return MD_ERR_CUDA;
     if (T <= MD_MAX_CONST_T) {
@@ -700,7 +708,7 @@ extern "C" __attribute__((visibility("default"))) int md_layernorm_bf16(const vo
     const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(resid);
-    static const bool hoist = getenv("MD_LN_HOIST") ? atoi(getenv("MD_LN_HOIST")) != 0 : true;
+    static const bool hoist = env_int("MD_LN_HOIST", 1) != 0;
     switch (H / 256) {
         case 1: layernorm_kernel<1, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
         case 2: layernorm_kernel<2, true><<<grid, 256, 0, stream>>>(i, r, gamma, beta, eps, o, M); break;
@@ -724,7 +732,7 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
                                  int64_t mask_d_stride, const float* x_start, float* x_out, void* out_bf16,
                                  float* pred_out, float* mean_out, int B, int L, int D, int mode, float eta, int clip,
                                  float top_p, cudaStream_t stream) {
-    if (g_sched_T == 0) { set_last_error("md_posterior_step: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (sched_state().T == 0) { set_last_error("md_posterior_step: md_set_schedule has not been called on this device"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_posterior_step: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((idx == nullptr) == (pred_in == nullptr)) { set_last_error("md_posterior_step: exactly one of idx / pred_in"); return MD_ERR_ARG; }
     if (idx != nullptr && E == nullptr) { set_last_error("md_posterior_step: idx needs E"); return MD_ERR_ARG; }
@@ -769,7 +777,7 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
 
 extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L,
                                   int D, cudaStream_t stream) {
-    if (g_sched_T == 0) { set_last_error("md_xstart_from_eps: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (sched_state().T == 0) { set_last_error("md_xstart_from_eps: md_set_schedule has not been called on this device"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_xstart_from_eps: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
     xstart_from_eps_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(x_t, eps, t, t_stride ? 1 : 0, out, B, L, D, vec_shift(D), sched_ref());
@@ -779,13 +787,13 @@ extern "C" __attribute__((visibility("default"))) int md_xstart_from_eps(const f
 extern "C" __attribute__((visibility("default"))) int md_q_sample(const float* x0, const float* noise, uint64_t seed, uint64_t step_counter, int64_t seq_offset,
                            const int32_t* t, int t_stride, const int32_t* mask, int64_t mask_tok_stride,
                            int64_t mask_d_stride, float* out, void* out_bf16, int B, int L, int D, cudaStream_t stream) {
-    if (t != nullptr && g_sched_T == 0) { set_last_error("md_q_sample: md_set_schedule has not been called"); return MD_ERR_ARG; }
+    if (t != nullptr && sched_state().T == 0) { set_last_error("md_q_sample: md_set_schedule has not been called on this device"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_q_sample: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
     QSampleArgs a;
     a.x0 = x0; a.noise = noise; a.t = t; a.t_stride = t_stride ? 1 : 0; a.mask = mask; a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride;
     a.out = out; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
-    a.rng.init(seed, step_counter, 0.0f); a.sched_dev = g_sched_dev; a.T = g_sched_T; a.vshift = vec_shift(D);
+    a.rng.init(seed, step_counter, 0.0f); a.sched_dev = sched_state().dev; a.T = sched_state().T; a.vshift = vec_shift(D);
     q_sample_kernel<<<ew_grid((int64_t)B * L * (D / 4), 256), 256, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "q_sample launch");
 }

@@ -10,6 +10,10 @@
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 // warps 2..9 = epilogue (TMEM -> registers -> bias / GELU / tanh / pos+time -> swizzled smem slab -> TMA store).
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "musediff_b200.h"
@@ -317,10 +321,47 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
+// Encoded tensor maps are cached per (base pointer, geometry): the sampling loop re-issues the same ~250 (pointer, shape)
+// pairs every step (fixed workspace, fixed weights), and cuTensorMapEncodeTiled costs more host time than a small-batch
+// kernel takes to run.  Device pointers are unique across devices (UVA), so one process-wide table is per-device safe.
+struct TmapKey {
+    const void* base;
+    uint64_t d[3], s[2];
+    uint32_t box[2], kind;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+        return (size_t)h;
+    }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* tm) {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmap_cache.find(k);
+    if (it == g_tmap_cache.end()) return false;
+    *tm = it->second;
+    return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& tm) {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+    g_tmap_cache[k] = tm;
+}
+
 // 2-D row-major [rows, cols] tensor (bf16 or fp32), box = [box_rows, box_cols] with box_cols * elem = 128 B, 128B swizzle.
 int make_tmap_2d(CUtensorMap* tm, const void* base, int is_f32, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                  uint32_t box_rows, uint32_t box_cols) {
     const bool sw64 = (box_cols * (is_f32 ? 4u : 2u)) == 64u;      // 64-byte box rows use the 64B swizzle, else 128B
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base; key.d[0] = cols; key.d[1] = rows; key.s[0] = row_stride_elems; key.box[0] = box_cols; key.box[1] = box_rows;
+    key.kind = is_f32 ? 1u : 0u;
+    if (tmap_lookup(key, tm)) return MD_OK;
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
@@ -336,12 +377,18 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int is_f32, uint64_t rows, u
                        box_cols, base);
         return MD_ERR_CUDA;
     }
+    tmap_store(key, *tm);
     return MD_OK;
 }
 
 // 3-D bf16 tensor [d2][d1][d0] (d0 contiguous), box = [1, box1, box0], 128B swizzle; rows beyond d1 read as zero.
 int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                       uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base; key.d[0] = d0; key.d[1] = d1; key.d[2] = d2; key.s[0] = stride1_elems; key.s[1] = stride2_elems;
+    key.box[0] = box0; key.box[1] = box1; key.kind = 2u;
+    if (tmap_lookup(key, tm)) return MD_OK;
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return MD_ERR_CUDA; }
     cuuint64_t gdim[3] = {d0, d1, d2};
@@ -356,18 +403,28 @@ int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d
                        (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, base);
         return MD_ERR_CUDA;
     }
+    tmap_store(key, *tm);
     return MD_OK;
 }
 
-static int g_num_sms = 0;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+static int g_num_sms[kMaxDevices] = {0};
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    const int dev = current_device();
+    if (g_num_sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms[dev] = n > 0 ? n : 148;
     }
-    return g_num_sms;
+    return g_num_sms[dev];
+}
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 template <int BN, int EPI, bool OUT_F32>
@@ -375,13 +432,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_kernel<BN, EPI, OUT_F32>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
-                       "cudaFuncSetAttribute(gemm)"))
-            return MD_ERR_CUDA;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {false};
+    if (ensure_dyn_smem(kern, Cfg::kSmemBytes, attr_set, "cudaFuncSetAttribute(gemm)")) return MD_ERR_CUDA;
     const int n_tiles = (args.N + BN - 1) / BN, m_tiles = (args.M + BM - 1) / BM;
     const int grid = min(n_tiles * m_tiles, num_sms());
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, args);
@@ -393,13 +445,8 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
                             cudaStream_t stream) {
     using Cfg = GemmCfg<256, true>;
     auto kern = gemm_pair_kernel<EPI, OUT_F32>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
-                       "cudaFuncSetAttribute(gemm pair)"))
-            return MD_ERR_CUDA;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {false};
+    if (ensure_dyn_smem(kern, Cfg::kSmemBytes, attr_set, "cudaFuncSetAttribute(gemm pair)")) return MD_ERR_CUDA;
     const int n_tiles = (args.N + 255) / 256, m_tiles = (args.M + 255) / 256;
     int pairs = num_sms() / 2;
     if (n_tiles * m_tiles < pairs) pairs = n_tiles * m_tiles;
@@ -448,8 +495,7 @@ extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void*
     }
     const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
     // CTA pairs (cta_group::2) for the large regular shapes; MD_GEMM_PAIR=0 forces the single-CTA kernel
-    static int use_pair = -1;
-    if (use_pair < 0) { const char* e = getenv("MD_GEMM_PAIR"); use_pair = e ? atoi(e) : 1; }
+    static const int use_pair = env_int("MD_GEMM_PAIR", 1);
     const bool pair = use_pair && N % 256 == 0 && M >= 1024 && !out_is_f32;
     CUtensorMap tmA, tmB, tmC;
     if (int e = make_tmap_2d(&tmA, A, 0, M, K, K, BM, BK)) return e;
@@ -458,10 +504,11 @@ extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void*
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
     a.bias = bias; a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;
-    { const char* e = getenv("MD_GEMM_DEBUG_SKIP"); a.debug_skip = e ? atoi(e) : 0; }
+    static const int debug_skip = env_int("MD_GEMM_DEBUG_SKIP", 0), idle_env = env_int("MD_GEMM_IDLE", -1);
+    a.debug_skip = debug_skip;
     // sleeping waits (try_wait suspend hint) for the warps that wait long: the TMA producer always, the epilogue warps when the
     // mainloop is long (K >= 2048: FFN2 +2..5 %); the epilogue-bound K = 768 shapes keep the polling wait (measured -1 % asleep)
-    { const char* e = getenv("MD_GEMM_IDLE"); a.idle_wait = e ? atoi(e) : (K >= 2048 ? 3 : 1); }
+    a.idle_wait = idle_env >= 0 ? idle_env : (K >= 2048 ? 3 : 1);
     if (pair) return dispatch_epi_pair<false>(epilogue, tmA, tmB, tmC, a, stream);
     if (BN == 256) return out_is_f32 ? dispatch_epi<256, true>(epilogue, tmA, tmB, tmC, a, stream)
                                      : dispatch_epi<256, false>(epilogue, tmA, tmB, tmC, a, stream);

@@ -271,13 +271,10 @@ extern "C" __attribute__((visibility("default"))) int md_round_argmin_tc(const f
     if (int e = make_tmap_2d(&tmB, E2, 0, (uint64_t)Vp, 2 * D, 2 * D, RT_BN, RT_BK)) return e;
     RoundTcArgs a;
     a.M = M; a.V = V; a.Vp = Vp; a.D = D; a.cst = cst; a.idx = idx; a.margin = margin;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (check_cuda(cudaFuncSetAttribute(round_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM), "cudaFuncSetAttribute(round_tc)") ||
-            check_cuda(cudaFuncSetAttribute(round_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM), "cudaFuncSetAttribute(round_tc)"))
-            return MD_ERR_CUDA;
-        attr_set = true;
-    }
+    static bool attr0[kMaxDevices] = {false}, attr1[kMaxDevices] = {false};
+    if (ensure_dyn_smem(round_tc_kernel<0>, RT_SMEM, attr0, "cudaFuncSetAttribute(round_tc)") ||
+        ensure_dyn_smem(round_tc_kernel<1>, RT_SMEM, attr1, "cudaFuncSetAttribute(round_tc)"))
+        return MD_ERR_CUDA;
     const int m_tiles = (int)((M + RT_BM - 1) / RT_BM);
     const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
     if (mode == 0) round_tc_kernel<0><<<grid, RT_THREADS, RT_SMEM, stream>>>(tmA, tmB, a);

@@ -149,13 +149,8 @@ template <int MODE>
 static int launch_round(const float* x, const float* E, const float* bias, int32_t* idx, float* margin, int64_t M, int V,
                         cudaStream_t stream) {
     auto kern = round_kernel<MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRoundSmem),
-                       "cudaFuncSetAttribute(round)"))
-            return MD_ERR_CUDA;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {false};
+    if (ensure_dyn_smem(kern, kRoundSmem, attr_set, "cudaFuncSetAttribute(round)")) return MD_ERR_CUDA;
     const int64_t grid = (M + RT - 1) / RT;
     kern<<<(unsigned)grid, kRoundThreads, kRoundSmem, stream>>>(x, E, bias, idx, margin, M, V);
     return check_cuda(cudaGetLastError(), "round launch");

@@ -97,6 +97,7 @@ class GaussianDiffusion:
     """Sampling utilities with the reference's attribute and method names (diffusion.py:121-901)."""
 
     noise_source = None     # optional callable(shape, kind) -> CUDA float tensor; None = in-kernel Philox
+    rounding_trace = None   # optional list: every fused rounding call appends (ids int32 [M], top-2 margin fp32 [M]) clones
     seq_offset = 0          # global index of this rank's first sequence (keeps Philox noise shard-invariant)
 
     def __init__(self, *, betas, predict_xstart, rescale_timesteps=False, training_mode="s2s"):
@@ -210,10 +211,14 @@ class GaussianDiffusion:
         if E is not None:
             # fused distance contraction + row argmin (rounding.py:21-28); tcgen05 split-bf16 kernel when the embedding
             # width allows it, fp32 CUDA-core kernel otherwise
+            trace = self.rounding_trace
             if E.shape[1] % 64 == 0:
-                idx = ops.round_argmin_tc(model_output, ops.split_embedding(E))
+                idx = ops.round_argmin_tc(model_output, ops.split_embedding(E), want_margin=trace is not None)
             else:
-                idx = ops.round_argmin(model_output, E)
+                idx = ops.round_argmin(model_output, E, want_margin=trace is not None)
+            if trace is not None:
+                idx, margin = idx
+                trace.append((idx.clone(), margin))
         elif denoised_fn is not None:
             pred = denoised_fn(model_output, t if t.numel() == B else t.expand(B))   # arbitrary user callable
         else:

@@ -28,9 +28,10 @@ def build_model_emb(model, device):
 
 @torch.no_grad()
 def sample_batch(model, diffusion, model_emb, cond, mode, step, diffusion_steps, strength=0.75, top_p=1, clamp_step=0,
-                 clip_denoised=True, device=None, fused_decode=True):
+                 clip_denoised=True, device=None, fused_decode=True, return_sample=False):
     """run/sample.py:177-220 for one batch: cond = {'input_ids', 'input_mask'} (host or device int tensors) ->
-    int64 token ids [B, L] on the device.  `fused_decode=False` keeps the reference's get_logits + argmax pair."""
+    int64 token ids [B, L] on the device.  `fused_decode=False` keeps the reference's get_logits + argmax pair;
+    `return_sample=True` also returns the final x_0 estimate `samples[-1]` (fp32 [B, L, D])."""
     device = device or next(model.parameters()).device
     input_ids = torch.as_tensor(cond["input_ids"]).to(device, non_blocking=True)
     mask_ori = torch.as_tensor(cond["input_mask"]).to(device, non_blocking=True)
@@ -58,8 +59,10 @@ def sample_batch(model, diffusion, model_emb, cond, mode, step, diffusion_steps,
                         t_enc=noising_t, only_last=True)                                # :200-215
     sample = samples[-1]
     if fused_decode:
-        return model.decode_tokens(sample)
-    return torch.argmax(model.get_logits(sample), dim=-1)                               # :219-220
+        tokens = model.decode_tokens(sample)
+    else:
+        tokens = torch.argmax(model.get_logits(sample), dim=-1)                         # :219-220
+    return (tokens, sample) if return_sample else tokens
 
 
 def load_training_args(model_path):

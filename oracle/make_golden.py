@@ -168,18 +168,47 @@ def golden_steps(seq_len=64, B=3, seed=3):
 
 def golden_loop(fname, mode, seq_len, B, seed, diffusion_steps, step, strength=0.75, top_p=1):
     """run/sample.py:177-220 replayed with reference objects (the data loader / MIDI tail are out of scope)."""
+    golden_loop_base(fname, mode, B, seed, diffusion_steps, step, strength=strength, top_p=top_p, seq_len=seq_len,
+                     store_x_noised=True)
+
+
+def golden_loop_base(fname, mode, B, seed, diffusion_steps, step, strength=1.0, top_p=1, seq_len=2096,
+                     store_x_noised=None):
+    """BASELINE.json configs[0] / configs[2] at the base sequence length: the driver slice run/sample.py:177-220 on
+    the unmodified reference, recording for EVERY rounding call (rounding.py:31-47, invoked at diffusion.py:322)
+    the chosen ids and the top-2 squared-distance margin, so the GPU parity test can apply the north-star rule
+    "tokens bit-exact except where the top-2 margin is below tolerance" over the whole chain.
+    x_noised is stored for modification mode (q_sample arithmetic); in generation mode it is a pure select of the
+    NoiseStream's first draw and the test regenerates it."""
+    import time
     import torch
-    from MuseDiffusion.models.rounding import denoised_fn_round
+    from MuseDiffusion.models.rounding import denoised_fn_round, get_efficient_knn
     p = O.make_random_params(seed=seed, seq_len=seq_len)
     model, diffusion, model_emb = build_reference(p, seq_len, diffusion_steps=diffusion_steps)
     cond = O.make_synthetic_batch(mode, B, seq_len, seed=seed + 5)
     ids = torch.from_numpy(cond["input_ids"])
     mask_ori = torch.from_numpy(cond["input_mask"])
     stream = O.NoiseStream(seed + 999)
+    rec_ids, rec_margin = [], []
+    inner = partial(denoised_fn_round, model_emb, dist=None)
+
+    def recording_round(x, t):
+        E = model_emb.weight
+        flat = x.reshape(-1, x.size(-1))
+        emb_norm = (E ** 2).sum(-1).view(-1, 1)
+        arr_norm = (flat ** 2).sum(-1).view(-1, 1)
+        dist = torch.clamp(emb_norm + arr_norm.transpose(0, 1) - 2.0 * torch.mm(E, flat.transpose(0, 1)), 0.0, np.inf)
+        two = torch.topk(-dist, k=2, dim=0)
+        rec_margin.append((two.values[0] - two.values[1]).numpy().astype(np.float32).reshape(x.shape[:-1]))
+        _, idx = get_efficient_knn(E, flat)
+        rec_ids.append(idx[0].numpy().astype(np.int16).reshape(x.shape[:-1]))
+        return inner(x, t)
+
     if step == diffusion_steps:
         gap, sample_fn = 1, diffusion.p_sample_loop
     else:
         gap, sample_fn = diffusion_steps // step, diffusion.ddim_sample_loop
+    t0 = time.time()
     with patched_randn_like(stream), torch.no_grad():
         x_start = model.get_embeds(ids)
         input_ids_mask = torch.broadcast_to(mask_ori.unsqueeze(dim=-1), x_start.shape)
@@ -192,16 +221,23 @@ def golden_loop(fname, mode, seq_len, B, seed, diffusion_steps, step, strength=0
             timestep = torch.full((B, 1), noising_t - 1)
             x_noised = diffusion.q_sample(x_start.unsqueeze(-1), timestep, mask=input_ids_mask).squeeze(-1)
         samples = sample_fn(model=model, shape=(B, seq_len, 128), noise=x_noised, clip_denoised=True,
-                            denoised_fn=partial(denoised_fn_round, model_emb, dist=None), model_kwargs=cond,
+                            denoised_fn=recording_round, model_kwargs=cond,
                             top_p=top_p, clamp_step=0, clamp_first=True, mask=input_ids_mask, x_start=x_start,
                             gap=gap, t_enc=noising_t, only_last=True)
         sample = samples[-1]
-        tokens = torch.argmax(model.get_logits(sample), dim=-1)
+        logits = model.get_logits(sample)
+        tokens = torch.argmax(logits, dim=-1)
+        top2 = torch.topk(logits, k=2, dim=-1).values
+    if store_x_noised is None:
+        store_x_noised = mode != "generation"
+    extra = {"x_noised": x_noised.numpy()} if store_x_noised else {}
     np.savez_compressed(os.path.join(OUT, fname), seed=seed, seq_len=seq_len, mode=mode,
                         diffusion_steps=diffusion_steps, step=step, strength=strength, top_p=top_p,
-                        input_ids=cond["input_ids"], input_mask=cond["input_mask"], x_noised=x_noised.numpy(),
-                        final_sample=sample.numpy(), tokens=tokens.numpy())
-    print(fname, tokens.shape, tokens[0, :20].tolist())
+                        input_ids=cond["input_ids"], input_mask=cond["input_mask"],
+                        step_ids=np.stack(rec_ids), step_margin=np.stack(rec_margin),
+                        final_sample=sample.numpy(), tokens=tokens.numpy(),
+                        logit_margin=(top2[..., 0] - top2[..., 1]).numpy().astype(np.float32), **extra)
+    print(fname, tokens.shape, len(rec_ids), "rounding calls, %.0f s" % (time.time() - t0), tokens[0, :20].tolist())
 
 
 def golden_meta_prefix():
@@ -302,6 +338,24 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "merge":
         golden_merge_and_mask()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "loops":
+        import torch
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        golden_loop("loop_gen_ddpm.npz", "generation", 64, 2, 11, 40, 40)
+        golden_loop("loop_mod_ddpm.npz", "modification", 64, 3, 12, 40, 40, strength=0.75)
+        golden_loop("loop_mod_ddim.npz", "modification", 64, 2, 13, 2000, 20, strength=1.0)
+        golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "base":
+        # ~15 min on 8 cores: BASELINE.json configs[0] (modification, --step 100 => DDIM gap 20, strength 1.0) and a
+        # generation-mode DDPM chain (truncated noise, clamp every step) at the base sequence length
+        import torch
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        golden_loop_base("loop_base_gen_ddpm24.npz", "generation", 2, 21, 24, 24)
+        golden_loop_base("loop_base_mod_ddim100.npz", "modification", 2, 22, 2000, 100, strength=1.0)
         return
     import torch
     torch.manual_seed(0)

@@ -3,7 +3,8 @@ ORACLE — TEST INFRASTRUCTURE ONLY (build-container only).
 
 Import shim that lets the UNMODIFIED reference (`/root/reference`, read-only, Python) import in
 this container so that `oracle/make_golden.py` can generate the fixtures under `tests/golden/`.
-`/root/reference` does not exist on the GPU box; nothing that runs there imports this file.
+`/root/reference` does not exist on the GPU box; there the verbatim copy `oracle/_ref/` (oracle/build_ref.sh, git-ignored)
+is used by the drop-in test and by bench.py's reference arm.
 
 Why each patch is needed is recorded in SURVEY.md §8c / Appendix A:
   * `AutoConfig.from_pretrained('bert-base-uncased')` (MuseDiffusion/models/network.py:44) needs the
@@ -15,7 +16,10 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MUSEDIFFUSION_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the build container has the read-only tree; the GPU box only has the verbatim copy made by oracle/build_ref.sh
+REFERENCE_ROOT = os.environ.get("MUSEDIFFUSION_REFERENCE") or (
+    "/root/reference" if os.path.isdir("/root/reference/MuseDiffusion") else os.path.join(_HERE, "_ref"))
 
 
 def reference_available() -> bool:
