@@ -451,6 +451,43 @@ MD_DEVINL void umma_pv128_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, u
         : "memory");
 }
 
+//   half-width last key block: O[tmem_d] (+)= P[tmem_a] V over 64 keys: four K=16 MMAs, with / without the commit
+MD_DEVINL void umma_pv64_commit_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                  uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q, pt, p0;\n\t.reg .b64 db;\n\t.reg .b32 ta;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+        "add.u32 ta, %1, 8;\n\tadd.u64 db, %2, 128;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 16;\n\tadd.u64 db, %2, 256;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 24;\n\tadd.u64 db, %2, 384;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(smem_u32(bar))
+        : "memory");
+}
+MD_DEVINL void umma_pv64_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred q, pt, p0;\n\t.reg .b64 db;\n\t.reg .b32 ta;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+        "add.u32 ta, %1, 8;\n\tadd.u64 db, %2, 128;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 16;\n\tadd.u64 db, %2, 256;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "add.u32 ta, %1, 24;\n\tadd.u64 db, %2, 384;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor")
 // ----------------------------------------------------------------------------------------------

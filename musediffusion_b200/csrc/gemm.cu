@@ -407,6 +407,10 @@ int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d
     return MD_OK;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 int current_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
@@ -418,13 +422,12 @@ int num_sms() {
     if (g_num_sms[dev] == 0) {
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        g_num_sms[dev] = n > 0 ? n : 148;
+        n = n > 0 ? n : 148;
+        static const int cap = env_int("MD_NUM_SMS", 0);     // tuning tools only (tools/clock_timeline.py leaves one SM to its probe)
+        if (cap > 0 && cap < n) n = cap;
+        g_num_sms[dev] = n;
     }
     return g_num_sms[dev];
-}
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
 }
 
 template <int BN, int EPI, bool OUT_F32>

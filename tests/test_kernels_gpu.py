@@ -77,7 +77,12 @@ def test_linear_argument_errors():
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("B,L,NH", [(1, 64, 2), (2, 128, 12), (2, 200, 12), (1, 256, 3), (3, 300, 4), (2, 2096, 12)])
+# L picks the work-item kinds and tail paths of the kernel: 64 / 128 SINGLE (one Q tile, one key block; half-width /
+# full last block), 130 / 200 / 256 PAIR only (last key block with 2 / 72 / 128 keys), 300 / 320 / 385 PAIR + SPLIT with a
+# half-width tail (44 / 64 / 1 keys), 2048 all PAIR no tail, 2096 the base shape (8 PAIR + SPLIT, 48-key tail, 48-row last
+# Q tile), 2176 = 17 x 128 SPLIT with a full tail, 4192 the scaled config (SPLIT, 96-key masked full-width tail)
+@pytest.mark.parametrize("B,L,NH", [(1, 64, 2), (2, 128, 12), (2, 130, 3), (2, 200, 12), (1, 256, 3), (3, 300, 4), (2, 320, 2),
+                                    (2, 385, 5), (2, 2048, 3), (2, 2096, 12), (1, 2176, 4), (1, 4192, 2)])
 def test_attention(B, L, NH):
     H = NH * 64
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + L + NH)
