@@ -116,13 +116,20 @@ int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x
  * element index (seq_offset*L + m)*D + d), truncated to |n| <= top_p by inverse-CDF when top_p > 0 (the law the
  * reference's rejection loop :378-385 samples).  t: int32 schedule index, t[b * t_stride] (t_stride 1 = per sequence,
  * 0 = one value for the batch, as inside the loops :516,887).  mask: int32, indexed m*mask_tok_stride + d*mask_d_stride
- * (NULL = no mask).  Optional outputs: out_bf16 = bf16 copy of x' (next step's GEMM operand), pred_out = processed
+ * (NULL = no mask).  step_counter_dev (optional): the step counter is read from this device word instead of the argument.
+ * Optional outputs: out_bf16 = bf16 copy of x' (next step's GEMM operand), pred_out = processed
  * pred_xstart, mean_out = the mean before noise ("greedy_mean" of p_sample). */
 int md_posterior_step(const float* x_t, const int32_t* idx, const float* pred_in, const float* E, const float* noise,
                       uint64_t seed, uint64_t step_counter, int64_t seq_offset, const int32_t* t, int t_stride,
                       const int32_t* mask, int64_t mask_tok_stride, int64_t mask_d_stride, const float* x_start,
                       float* x_out, void* out_bf16, float* pred_out, float* mean_out, int B, int L, int D, int mode,
-                      float eta, int clip, float top_p, cudaStream_t stream);
+                      float eta, int clip, float top_p, const uint64_t* step_counter_dev, cudaStream_t stream);
+/* Loop state on the device, so that ONE captured CUDA graph of a reverse step can be replayed for every index of the
+ * loops diffusion.py:508-540 / :878-901 (the reference rebuilds t = th.tensor([i] * B) on the host every iteration):
+ * k = *cursor; *t_cur = t_idx[k]; *tm_cur = t_model[k] (the value _WrappedModel feeds the denoiser, :1027-1032);
+ * *ctr_cur = ctr_base + k (Philox counter of md_posterior_step's step_counter_dev); *cursor = k + 1.  n = entries. */
+int md_step_advance(int32_t* cursor, const int32_t* t_idx, const float* t_model, int n, int32_t* t_cur, float* tm_cur,
+                    uint64_t* ctr_cur, uint64_t ctr_base, cudaStream_t stream);
 /* x0 = sqrt_recip[t] x_t - sqrt_recipm1[t] eps  (_predict_xstart_from_eps, diffusion.py:194-199), for
  * predict_xstart = False models. */
 int md_xstart_from_eps(const float* x_t, const float* eps, const int32_t* t, int t_stride, float* out, int B, int L,

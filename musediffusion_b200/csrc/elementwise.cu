@@ -137,10 +137,12 @@ struct NoiseGen {
     }
     // four normals for the aligned group of 4 elements starting at global element index 4*g
     template <bool kCentral>
-    MD_DEVINL float4 draw4t(uint64_t g) const {
-        const uint4 r = philox(make_uint4((uint32_t)g, (uint32_t)(g >> 32), step_lo, step_hi));
+    MD_DEVINL float4 draw4t(uint64_t g, uint32_t slo, uint32_t shi) const {      // step counter supplied by the caller
+        const uint4 r = philox(make_uint4((uint32_t)g, (uint32_t)(g >> 32), slo, shi));
         return make_float4(one<kCentral>(r.x), one<kCentral>(r.y), one<kCentral>(r.z), one<kCentral>(r.w));
     }
+    template <bool kCentral>
+    MD_DEVINL float4 draw4t(uint64_t g) const { return draw4t<kCentral>(g, step_lo, step_hi); }
     MD_DEVINL float4 draw4(uint64_t g) const { return central ? draw4t<true>(g) : draw4t<false>(g); }
 };
 
@@ -207,7 +209,17 @@ struct StepArgs {
     int clip;
     NoiseGen rng;
     SchedRef sched;
+    const unsigned long long* step_dev;   // optional: Philox step counter read from device memory (CUDA-graph replays)
 };
+MD_DEVINL void step_counter_of(const StepArgs& a, uint32_t& lo, uint32_t& hi) {
+    lo = a.rng.step_lo;
+    hi = a.rng.step_hi;
+    if (a.step_dev != nullptr) {
+        const unsigned long long s = *a.step_dev;
+        lo = (uint32_t)s;
+        hi = (uint32_t)(s >> 32);
+    }
+}
 
 MD_DEVINL float clampf(float v, int clip) { return clip ? fminf(fmaxf(v, -1.0f), 1.0f) : v; }
 
@@ -257,6 +269,8 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
     const bool uniform_t = (a.t_stride == 0);
     StepCoef ku;
     if (uniform_t) ku = step_coef<MODE>(a.sched, a.t[0], a.eta);
+    uint32_t slo, shi;
+    step_counter_of(a, slo, shi);
     for (IdxT i0 = (IdxT)blockIdx.x * (IdxT)blockDim.x + (IdxT)threadIdx.x; i0 < total; i0 += nthreads * kStepUnroll) {
         IdxT off[kStepUnroll], tok[kStepUnroll];
         int bq[kStepUnroll], dd[kStepUnroll];
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
             p.x = clampf(p.x, a.clip); p.y = clampf(p.y, a.clip); p.z = clampf(p.z, a.clip); p.w = clampf(p.w, a.clip);
             if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off[u], p);
             const float4 nn = (NOISE == 0) ? n[u]
-                              : a.rng.template draw4t<NOISE == 1>((uint64_t)(((a.seq_offset * a.L) * a.D + (int64_t)off[u]) >> 2));
+                              : a.rng.template draw4t<NOISE == 1>((uint64_t)(((a.seq_offset * a.L) * a.D + (int64_t)off[u]) >> 2), slo, shi);
             float4 mu;
             mu.x = step_mean<MODE>(k, x[u].x, p.x);
             mu.y = step_mean<MODE>(k, x[u].y, p.y);
@@ -343,6 +357,8 @@ __global__ void __launch_bounds__(256) posterior_step_d128_kernel(const StepArgs
     const bool uniform_t = (a.t_stride == 0);
     StepCoef ku;
     if (uniform_t) ku = step_coef<MODE>(a.sched, a.t[0], a.eta);
+    uint32_t slo, shi;
+    step_counter_of(a, slo, shi);
     const uint64_t g_base = (uint64_t)(a.seq_offset * a.L) * 32u + (uint32_t)lane;     // float4 index of token 0, this lane
     for (int tok0 = warp_global * kStepUnroll; tok0 < M; tok0 += nwarps * kStepUnroll) {
         float4 x[kStepUnroll], pr[kStepUnroll], n[kStepUnroll];
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(256) posterior_step_d128_kernel(const StepArgs
             // sigma == 0 (DDIM with eta = 0, or t == 0): the product sc * n is exactly 0 for any finite n -> skip the RNG
             float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
             if (NOISE == 0) nn = n[u];
-            else if (sc != 0.0f) nn = a.rng.template draw4t<NOISE == 1>(g_base + (uint64_t)tok * 32u);
+            else if (sc != 0.0f) nn = a.rng.template draw4t<NOISE == 1>(g_base + (uint64_t)tok * 32u, slo, shi);
             float4 mu;
             mu.x = step_mean<MODE>(k, x[u].x, p.x);
             mu.y = step_mean<MODE>(k, x[u].y, p.y);
@@ -647,7 +663,30 @@ static int ew_grid(int64_t work_items, int threads) {
 using namespace md;
 
 extern "C" __attribute__((visibility("default"))) const char* md_last_error(void) { return g_err; }
-extern "C" __attribute__((visibility("default"))) int md_abi_version(void) { return 1; }
+extern "C" __attribute__((visibility("default"))) int md_abi_version(void) { return 2; }
+
+// Device-resident loop state for CUDA-graph replays of one reverse step: the graph is captured once and every replay reads
+// its schedule index / model timestep / Philox counter from device memory.  One thread: k = *cursor;
+// t_cur = t_idx[min(k, n-1)], tm_cur = t_model[min(k, n-1)], ctr_cur = ctr_base + k, *cursor = k + 1.
+__global__ void step_advance_kernel(int32_t* cursor, const int32_t* t_idx, const float* t_model, int n, int32_t* t_cur,
+                                    float* tm_cur, unsigned long long* ctr_cur, unsigned long long ctr_base) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int k = *cursor;
+    const int kk = k < n ? k : n - 1;
+    *t_cur = t_idx[kk];
+    *tm_cur = t_model[kk];
+    *ctr_cur = ctr_base + (unsigned long long)k;
+    *cursor = k + 1;
+}
+extern "C" __attribute__((visibility("default"))) int md_step_advance(int32_t* cursor, const int32_t* t_idx, const float* t_model, int n, int32_t* t_cur,
+                               float* tm_cur, uint64_t* ctr_cur, uint64_t ctr_base, cudaStream_t stream) {
+    if (cursor == nullptr || t_idx == nullptr || t_model == nullptr || t_cur == nullptr || tm_cur == nullptr || ctr_cur == nullptr || n <= 0) {
+        set_last_error("md_step_advance: null pointer or empty schedule (n=%d)", n);
+        return MD_ERR_ARG;
+    }
+    step_advance_kernel<<<1, 32, 0, stream>>>(cursor, t_idx, t_model, n, t_cur, tm_cur, reinterpret_cast<unsigned long long*>(ctr_cur), ctr_base);
+    return check_cuda(cudaGetLastError(), "step_advance launch");
+}
 
 extern "C" __attribute__((visibility("default"))) int md_set_schedule(const float* tables, int T, cudaStream_t stream) {
     if (tables == nullptr || T <= 0) { set_last_error("md_set_schedule: bad arguments (T=%d)", T); return MD_ERR_ARG; }
@@ -731,7 +770,7 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
                                  const int32_t* t, int t_stride, const int32_t* mask, int64_t mask_tok_stride,
                                  int64_t mask_d_stride, const float* x_start, float* x_out, void* out_bf16,
                                  float* pred_out, float* mean_out, int B, int L, int D, int mode, float eta, int clip,
-                                 float top_p, cudaStream_t stream) {
+                                 float top_p, const uint64_t* step_counter_dev, cudaStream_t stream) {
     if (sched_state().T == 0) { set_last_error("md_posterior_step: md_set_schedule has not been called on this device"); return MD_ERR_ARG; }
     if (D % 4 != 0) { set_last_error("md_posterior_step: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((idx == nullptr) == (pred_in == nullptr)) { set_last_error("md_posterior_step: exactly one of idx / pred_in"); return MD_ERR_ARG; }
@@ -746,6 +785,7 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     a.mask_tok_stride = mask_tok_stride; a.mask_d_stride = mask_d_stride; a.x_start = x_start; a.x_out = x_out;
     a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.seq_offset = seq_offset; a.B = B; a.L = L; a.D = D;
     a.eta = eta; a.clip = clip; a.rng.init(seed, step_counter, top_p); a.sched = sched_ref(); a.vshift = vec_shift(D);
+    a.step_dev = reinterpret_cast<const unsigned long long*>(step_counter_dev);
     const int grid = ew_grid(((int64_t)B * L * (D / 4) + kStepUnroll - 1) / kStepUnroll, 256);
     const int nz = (noise != nullptr) ? 0 : (a.rng.central ? 1 : 2);
     if (D == 128 && (mask == nullptr || mask_d_stride == 0) && (int64_t)B * L < (1 << 24)) {

@@ -98,6 +98,8 @@ class GaussianDiffusion:
 
     noise_source = None     # optional callable(shape, kind) -> CUDA float tensor; None = in-kernel Philox
     rounding_trace = None   # optional list: every fused rounding call appends (ids int32 [M], top-2 margin fp32 [M]) clones
+    use_cuda_graph = True   # loops of >= GRAPH_MIN_STEPS steps replay ONE captured CUDA graph of a reverse step (fast path only)
+    GRAPH_MIN_STEPS = 4
     seq_offset = 0          # global index of this rank's first sequence (keeps Philox noise shard-invariant)
 
     def __init__(self, *, betas, predict_xstart, rescale_timesteps=False, training_mode="s2s"):
@@ -298,9 +300,6 @@ class GaussianDiffusion:
             if x is None:
                 x = ops.fill_normal(tuple(shape), device, seed=self._seed(), step_counter=self._next_counter(),
                                     elem_offset=self.seq_offset * int(np.prod(shape[1:])))
-        if progress:
-            from tqdm.auto import tqdm
-            indices = tqdm(indices)
         fast = self._fast_model(model)
         B = shape[0]
         if len(indices) == 0:
@@ -315,21 +314,35 @@ class GaussianDiffusion:
         if x_start is not None:
             x_start = x_start.to(torch.float32).contiguous()
         x = x.to(torch.float32).contiguous()
-        t_idx = torch.tensor(list(indices), dtype=torch.int32, device=device)
+        idx_list = list(indices)
+        t_idx = torch.tensor(idx_list, dtype=torch.int32, device=device)
         t_model = self._model_timesteps(t_idx.long()).float()
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(idx_list)
+        else:
+            indices = idx_list
+
+        def rounds_at(i):
+            """clamp gating, diffusion.py:517-526 (the DDIM loop always rounds, :889-899)"""
+            if mode != _lib.STEP_DDPM:
+                return True
+            return (i >= clamp_step) if clamp_first else not (i > clamp_step)
+
+        E = rounding_weight_of(denoised_fn)
+        graph_ok = (fast is not None and self.use_cuda_graph and len(idx_list) >= self.GRAPH_MIN_STEPS and not want_aux
+                    and self.noise_source is None and self.rounding_trace is None and ops._PROFILE[0] is None
+                    and E is not None and E.shape[1] % 64 == 0 and all(rounds_at(i) for i in idx_list)
+                    and x.dim() == 3)
+        if graph_ok:
+            yield from self._graph_loop(mode, fast, x, E, t_idx, t_model, indices, clip_denoised, top_p, mask, x_start, eta)
+            return
         bufs = [torch.empty(tuple(shape), dtype=torch.float32, device=device) for _ in range(2)] if not want_aux else None
         xb = [torch.empty(tuple(shape), dtype=torch.bfloat16, device=device) for _ in range(2)] if fast is not None else None
         x_bf16 = None
         mo_buf = torch.empty(tuple(shape), dtype=torch.float32, device=device) if fast is not None else None
         for k, i in enumerate(indices):
-            if mode == _lib.STEP_DDPM:
-                # clamp gating, diffusion.py:517-526
-                if not clamp_first:
-                    fn = None if i > clamp_step else denoised_fn
-                else:
-                    fn = denoised_fn if i >= clamp_step else None
-            else:
-                fn = denoised_fn                                       # ddim loop always rounds (:889-899)
+            fn = denoised_fn if rounds_at(i) else None
             t1 = t_idx[k:k + 1]
             model_output = None
             if fast is not None:
@@ -342,6 +355,61 @@ class GaussianDiffusion:
             x = sample
             x_bf16 = None if xb is None else xb[k & 1]
             yield sample, pred, mean, t_arg
+
+    def _graph_loop(self, mode, fast, x, E, t_idx, t_model, indices, clip_denoised, top_p, mask, x_start, eta):
+        """The same chain with ONE reverse step captured as a CUDA graph and replayed.
+        What changes from step to step lives in device memory: `md_step_advance` (first node of the graph) moves a cursor
+        over the index tables and publishes the schedule index, the denoiser's timestep value and the Philox counter of
+        the step; the posterior kernel reads the counter from there, so the noise is bit-identical to the eager loop.
+        x_t is updated in place (the posterior kernel is elementwise) and its bf16 copy feeds the next step's first GEMM.
+        The first step runs eagerly (one-time set-up: shared-memory attributes, weight pack, tensor maps), the graph is
+        captured from the second one."""
+        dev = x.device
+        n = t_idx.numel()
+        B = x.shape[0]
+        self._upload_schedule()
+        x = x.clone()                                   # updated in place: never the caller's tensor
+        xb = ops.cast_bf16(x)
+        mo = torch.empty_like(x)
+        cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+        t_cur = torch.zeros(1, dtype=torch.int32, device=dev)
+        tm_cur = torch.zeros(1, dtype=torch.float32, device=dev)
+        ctr_cur = torch.zeros(1, dtype=torch.int64, device=dev)
+        ctr_base = self._noise_calls + 1                # the value _next_counter() hands to the first step of an eager loop
+        seed = self._seed()
+        se = ops.split_embedding(E)
+        idx = torch.empty((x.shape[0] * x.shape[1],), dtype=torch.int32, device=dev)
+        if mode == _lib.STEP_DDPM:
+            tp = top_p if (top_p is not None and top_p > 0) else 0.0
+        else:
+            tp = 0.0                                    # ddim_sample ignores top_p (diffusion.py:738)
+
+        def one_step():
+            ops.step_advance(cursor, t_idx, t_model, t_cur, tm_cur, ctr_cur, ctr_base)
+            out = fast.denoise(x, tm_cur, x_bf16=xb, uniform_t=True, out=mo)
+            if not self.predict_xstart:
+                out = ops.xstart_from_eps(x, out, t_cur)
+            ops.round_argmin_tc(out, se, out=idx)
+            ops.posterior_step(x, t_cur, mode, idx=idx, E=E, seed=seed, seq_offset=self.seq_offset, mask=mask, x_start=x_start,
+                               eta=eta, clip=clip_denoised, top_p=tp, out=x, out_bf16=xb, step_counter_dev=ctr_cur)
+
+        graph, nodes = None, 0
+        for k, i in enumerate(indices):
+            if k == 0:
+                one_step()
+            else:
+                if graph is None:
+                    before = ops.launch_count()
+                    torch.cuda.synchronize(dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        one_step()
+                    nodes = ops.launch_count() - before          # kernels recorded by the capture (nothing ran yet)
+                    ops.add_launches(-nodes)
+                graph.replay()
+                ops.add_launches(nodes)
+            self._noise_calls += 1
+            yield x, None, None, t_idx[k:k + 1]
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                       device=None, progress=False, top_p=None, clamp_step=None, clamp_first=None, mask=None,

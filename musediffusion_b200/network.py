@@ -263,6 +263,11 @@ class TransformerNetModel(nn.Module):
         E = _lib
         xb = x_bf16.view(M, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(M, D).float())
         t = timesteps.reshape(-1).float()
+        if not uniform_t:
+            if t.numel() == 1:
+                uniform_t = True                  # one timestep for the whole batch (GaussianDiffusion._step allows it)
+            elif t.numel() != B:                  # the reference asserts t.shape == (B,) (network.py:137 via timestep_embedding)
+                raise ValueError("timesteps has %d entries for a batch of %d sequences" % (t.numel(), B))
         temb = ops.timestep_mlp(t[:1] if uniform_t else t, pk.t0_w, pk.t0_b, pk.t2_w, pk.t2_b)
         ops.linear(xb, pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=ws.a)
         ops.linear(ws.a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,

@@ -1,35 +1,27 @@
-"""Tensor-level wrappers over the C-ABI kernels (ctypes; one wrapper per `md_*` entry of include/musediff_b200.h).
-
-Every function here launches hand-written sm_100a kernels on the current CUDA stream; inputs must be CUDA tensors
+"""Tensor-level wrappers over the custom ops `torch.ops.musediff.*` (custom_ops.py: one op per `md_*` kernel entry of
+include/musediff_b200.h, CUDA dispatch key only).  The wrappers allocate outputs, check dtype / layout / device and
+then dispatch; every op launches hand-written sm_100a kernels on the current CUDA stream.  Inputs must be CUDA tensors
 (a CPU tensor raises — there is no fallback)."""
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, custom_ops
+from .custom_ops import _s64
 
 BF16 = torch.bfloat16
+K = custom_ops.ops          # torch.ops.musediff
 
-_LAUNCHES = [0]
-_PROFILE = [None]      # list of (name, detail, start_event, end_event) while profile_step() is active
-
-
-def call(name, *args, detail=""):
-    """one C-ABI call == one kernel launch of ours (md_set_schedule only copies tables)."""
-    prof = _PROFILE[0]
-    if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.call(name, *args)
-        e1.record()
-        prof.append((name, detail, e0, e1))
-    else:
-        _lib.call(name, *args)
-    if name != "md_set_schedule":
-        _LAUNCHES[0] += 1
+_LAUNCHES = custom_ops._LAUNCHES
+_PROFILE = custom_ops._PROFILE      # list of (name, detail, start_event, end_event) while profile_step() is active
 
 
 def launch_count():
     return _LAUNCHES[0]
+
+
+def add_launches(n):
+    """kernels launched by a CUDA-graph replay (they do not pass through the op layer)."""
+    _LAUNCHES[0] += int(n)
 
 
 def profile_step(fn):
@@ -53,6 +45,13 @@ def _p(t):
     if not t.is_cuda:
         raise _lib.MuseDiffLibraryError("musediffusion_b200 ops need CUDA tensors (got a %s tensor)" % t.device)
     return t.data_ptr()
+
+
+def _cu(*tensors):
+    """every tensor handed to an op lives on a CUDA device (the ops have no other backend)."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.MuseDiffLibraryError("musediffusion_b200 ops need CUDA tensors (got a %s tensor)" % t.device)
 
 
 def _c(t, dtype=None):
@@ -80,7 +79,7 @@ def set_schedule(tables64, key=None):
     T = len(tables64[TABLE_ORDER[0]])
     host = np.ascontiguousarray(np.stack([np.asarray(tables64[n], dtype=np.float64).astype(np.float32)
                                           for n in TABLE_ORDER]))
-    call("md_set_schedule", host.ctypes.data, T, _stream())
+    _lib.call("md_set_schedule", host.ctypes.data, T, _stream())      # host -> device table copy, not a kernel op
     _current_schedule_key[torch.cuda.current_device()] = key
 
 
@@ -88,7 +87,8 @@ def set_schedule(tables64, key=None):
 def cast_bf16(x):
     x = _c(x, torch.float32)
     out = torch.empty(x.shape, dtype=BF16, device=x.device)
-    call("md_cast_f32_bf16", _p(x), _p(out), x.numel(), _stream())
+    _cu(x)
+    K.cast_f32_bf16(x, out)
     return out
 
 
@@ -98,17 +98,17 @@ def embed_gather(E, ids):
         ids = ids.to(torch.int64)
     ids = _c(ids)
     out = torch.empty(tuple(ids.shape) + (E.shape[1],), dtype=torch.float32, device=E.device)
-    call("md_embed_gather", _p(E), _p(ids), int(ids.dtype == torch.int64), _p(out), ids.numel(), E.shape[0],
-         E.shape[1], _stream())
+    _cu(E, ids)
+    K.embed_gather(E, ids, out)
     return out
 
 
 def timestep_mlp(t, W0, b0, W2, b2):
     t = _c(t, torch.float32)
+    _cu(t, W0, b0, W2, b2)
     out = torch.empty((t.numel(), W2.shape[0]), dtype=torch.float32, device=t.device)
     hid = torch.empty((t.numel(), W0.shape[0]), dtype=torch.float32, device=t.device)
-    call("md_timestep_mlp", _p(t), _p(W0), _p(b0), _p(W2), _p(b2), _p(out), _p(hid), t.numel(), W0.shape[1],
-         W0.shape[0], W2.shape[0], _stream())
+    K.timestep_mlp(t, W0, b0, W2, b2, out, hid)
     return out
 
 
@@ -119,7 +119,10 @@ def layernorm(x, gamma, beta, eps, resid=None, out=None):
     H = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
-    call("md_layernorm_bf16", _p(x), _p(resid), _p(gamma), _p(beta), float(eps), _p(out), x.numel() // H, H, _stream())
+    if H % 256 != 0 or H > 2048:
+        raise _lib.MuseDiffLibraryError("md_layernorm_bf16: H=%d must be a multiple of 256, <= 2048" % H)
+    _cu(x, resid, gamma, beta, out)
+    K.layernorm_bf16(x, resid, gamma, beta, float(eps), out)
     return out
 
 
@@ -127,13 +130,13 @@ def layernorm(x, gamma, beta, eps, resid=None, out=None):
 def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, pos=None, temb=None, temb_stride=0, L=0, out=None):
     """out[M,N] = epi(A[M,K] @ W[N,K]^T + bias)."""
     assert A.dtype == BF16 and W.dtype == BF16 and A.is_contiguous() and W.is_contiguous()
-    M, K = A.shape
+    M, Kd = A.shape
     N = W.shape[0]
-    assert W.shape[1] == K
+    assert W.shape[1] == Kd
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=A.device)
-    call("md_linear_bf16", _p(A), _p(W), _p(bias), _p(out), M, N, K, epilogue, int(out.dtype == torch.float32),
-         _p(pos), _p(temb), temb_stride, L, _stream(), detail="%dx%dx%d epi=%d" % (M, N, K, epilogue))
+    _cu(A, W, bias, out, pos, temb)
+    K.linear_bf16(A, W, bias, out, epilogue, pos, temb, temb_stride, L)
     return out
 
 
@@ -142,7 +145,10 @@ def attention(qkv, B, L, NH, out=None):
     H = qkv.shape[-1] // 3
     if out is None:
         out = torch.empty((B * L, H), dtype=BF16, device=qkv.device)
-    call("md_attention_bf16", _p(qkv), _p(out), B, L, NH, H // NH, _stream())
+    if H // NH != 64:
+        raise _lib.MuseDiffLibraryError("md_attention_bf16: head dim %d unsupported (kernel is specialised for 64)" % (H // NH))
+    _cu(qkv, out)
+    K.attention_bf16(qkv, out, B, L, NH)
     return out
 
 
@@ -154,7 +160,8 @@ def round_argmin(x, E, want_margin=False):
     M = x.numel() // D
     idx = torch.empty((M,), dtype=torch.int32, device=x.device)
     margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
-    call("md_round_argmin", _p(x), _p(E), _p(idx), _p(margin), M, E.shape[0], D, _stream())
+    _cu(x, E)
+    K.round_argmin(x, E, idx, margin)
     return (idx, margin) if want_margin else idx
 
 
@@ -166,7 +173,8 @@ def logits_argmax(x, E, bias, want_margin=False):
     M = x.numel() // D
     tok = torch.empty((M,), dtype=torch.int32, device=x.device)
     margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
-    call("md_logits_argmax", _p(x), _p(E), _p(bias), _p(tok), _p(margin), M, E.shape[0], D, _stream())
+    _cu(x, E, bias)
+    K.logits_argmax(x, E, bias, tok, margin)
     return (tok, margin) if want_margin else tok
 
 
@@ -176,7 +184,8 @@ def split_bf16(x, copies=1):
     D = x.shape[-1]
     rows = x.numel() // D
     out = torch.empty((rows, copies * 2 * D), dtype=BF16, device=x.device)
-    call("md_split_bf16", _p(x), _p(out), rows, D, copies, _stream())
+    _cu(x)
+    K.split_bf16(x, out, copies)
     return out
 
 
@@ -190,7 +199,8 @@ class SplitEmbedding:
         self.Vp = _lib.lib.md_round_tc_padded_vocab(self.V)
         self.E2 = torch.empty((self.Vp, 2 * self.D), dtype=BF16, device=E.device)
         self.sqnorm = torch.empty((self.Vp,), dtype=torch.float32, device=E.device)
-        call("md_embed_split", _p(E), self.V, self.D, _p(self.E2), _p(self.sqnorm), _stream())
+        _cu(E)
+        K.embed_split(E, self.E2, self.sqnorm)
         self._ws = {}
 
     def logit_cst(self, bias):
@@ -229,8 +239,8 @@ def round_argmin_tc(x, se, cst=None, mode=0, want_margin=False, out=None):
     M = x.numel() // se.D
     idx = out if out is not None else torch.empty((M,), dtype=torch.int32, device=x.device)
     margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
-    call("md_round_argmin_tc", _p(x), _p(se.E2), _p(se.sqnorm if cst is None else cst), _p(se.workspace(M)), _p(idx),
-         _p(margin), M, se.V, se.D, mode, _stream())
+    _cu(x)
+    K.round_argmin_tc(x, se.E2, se.sqnorm if cst is None else cst, se.workspace(M), idx, margin, se.V, mode)
     return (idx, margin) if want_margin else idx
 
 
@@ -263,7 +273,7 @@ def _t_args(t, B):
 
 def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0, step_counter=0, seq_offset=0,
                    mask=None, x_start=None, eta=0.0, clip=True, top_p=0.0, out=None, out_bf16=None, pred_out=None,
-                   mean_out=None):
+                   mean_out=None, step_counter_dev=None):
     x_t = _c(x_t, torch.float32)
     B, L, D = x_t.shape
     t, t_stride = _t_args(t, B)
@@ -278,9 +288,11 @@ def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0
         x_start = _c(x_start, torch.float32)
     if idx is not None:
         idx = _c(idx, torch.int32)
-    call("md_posterior_step", _p(x_t), _p(idx), _p(pred), _p(E), _p(noise), int(seed), int(step_counter),
-         int(seq_offset), _p(t), t_stride, _p(mask_t), ts, ds, _p(x_start), _p(out), _p(out_bf16), _p(pred_out),
-         _p(mean_out), B, L, D, mode, float(eta), int(bool(clip)), float(top_p or 0.0), _stream())
+    if (idx is None) == (pred is None):
+        raise _lib.MuseDiffLibraryError("md_posterior_step: exactly one of idx / pred_in")
+    _cu(x_t, idx, pred, E, noise, t, mask_t, x_start, out, out_bf16, pred_out, mean_out, step_counter_dev)
+    K.posterior_step(x_t, idx, pred, E, noise, _s64(seed), _s64(step_counter), int(seq_offset), t, t_stride, mask_t, ts, ds, x_start,
+                     out, out_bf16, pred_out, mean_out, mode, float(eta), bool(clip), float(top_p or 0.0), step_counter_dev)
     return out
 
 
@@ -290,7 +302,8 @@ def xstart_from_eps(x_t, eps, t):
     B, L, D = x_t.shape
     out = torch.empty_like(x_t)
     t, t_stride = _t_args(t, B)
-    call("md_xstart_from_eps", _p(x_t), _p(eps), _p(t), t_stride, _p(out), B, L, D, _stream())
+    _cu(x_t, eps, t)
+    K.xstart_from_eps(x_t, eps, t, t_stride, out)
     return out
 
 
@@ -303,15 +316,17 @@ def q_sample(x0, t=None, noise=None, seed=0, step_counter=0, seq_offset=0, mask=
     if noise is not None:
         noise = _c(noise, torch.float32)
     tt, t_stride = _t_args(t, B) if t is not None else (None, 0)
-    call("md_q_sample", _p(x0), _p(noise), int(seed), int(step_counter), int(seq_offset), _p(tt), t_stride, _p(mask_t), ts, ds,
-         _p(out), _p(out_bf16), B, L, D, _stream())
+    _cu(x0, noise, tt, mask_t, out_bf16)
+    K.q_sample(x0, noise, _s64(seed), _s64(step_counter), int(seq_offset), tt, t_stride, mask_t, ts, ds, out, out_bf16)
     return out
 
 
 def fill_normal(shape, device, seed=0, step_counter=0, elem_offset=0, top_p=0.0):
     out = torch.empty(shape, dtype=torch.float32, device=device)
-    call("md_fill_normal", _p(out), out.numel(), int(seed), int(step_counter), int(elem_offset), float(top_p),
-         _stream())
+    if int(elem_offset) % 4 != 0:
+        raise _lib.MuseDiffLibraryError("md_fill_normal: elem_offset must be a multiple of 4")
+    _cu(out)
+    K.fill_normal(out, _s64(seed), _s64(step_counter), int(elem_offset), float(top_p))
     return out
 
 
@@ -326,8 +341,8 @@ def decode_prepare(tokens, mask, strict=False):
     note_len = torch.empty((B,), dtype=torch.int32, device=dev)
     notes = torch.empty((B, 2 * L), dtype=torch.int32, device=dev)
     meta = torch.empty((B, 11), dtype=torch.int32, device=dev)
-    call("md_decode_prepare", _p(tok), _p(msk), B, L, 1 if strict else 0, _p(status), _p(note_len), _p(notes), _p(meta),
-         _stream())
+    _cu(tok, msk)
+    K.decode_prepare(tok, msk, bool(strict), status, note_len, notes, meta)
     return status, note_len, notes, meta
 
 
@@ -343,8 +358,8 @@ def merge_and_mask(src, src_len, trg, trg_len, seq_len, end_token=1):
     input_ids = torch.empty((B, seq_len), dtype=torch.int32, device=dev)
     input_mask = torch.empty((B, seq_len), dtype=torch.int32, device=dev)
     length = torch.empty((B,), dtype=torch.int32, device=dev)
-    call("md_merge_and_mask", _p(src) if Ls else None, _p(src_len), _p(trg), _p(trg_len), B, Ls, Lt, int(seq_len), int(end_token),
-         _p(input_ids), _p(input_mask), _p(length), _stream())
+    _cu(src_len, trg, trg_len)
+    K.merge_and_mask(src if Ls else None, src_len, trg, trg_len, int(seq_len), int(end_token), input_ids, input_mask, length)
     return input_ids, input_mask, length
 
 
@@ -358,7 +373,8 @@ def sequence_metrics(notes, note_len, meta):
     vectors = torch.empty((B, 56), dtype=torch.float32, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
-    call("md_sequence_metrics", _p(notes), _p(note_len), _p(meta), B, Ln, _p(vectors), _p(status), _p(stats), _stream())
+    _cu(notes, note_len, meta)
+    K.sequence_metrics(notes, note_len, meta, vectors, status, stats)
     return vectors, status, stats
 
 
@@ -368,5 +384,12 @@ def onnc_nearest(vectors, want_msim=False):
     N = vectors.shape[0]
     most = torch.empty((N,), dtype=torch.int32, device=vectors.device)
     msim = torch.empty((N, N), dtype=torch.float32, device=vectors.device) if want_msim else None
-    call("md_onnc", _p(vectors), N, _p(msim), _p(most), _stream())
+    _cu(vectors)
+    K.onnc(vectors, msim, most)
     return most, msim
+
+
+def step_advance(cursor, t_idx, t_model, t_cur, tm_cur, ctr_cur, ctr_base):
+    """md_step_advance: device-resident loop state of the CUDA-graph replay (see diffusion.GaussianDiffusion._loop)."""
+    _cu(cursor, t_idx, t_model, t_cur, tm_cur, ctr_cur)
+    K.step_advance(cursor, t_idx, t_model, t_cur, tm_cur, ctr_cur, _s64(ctr_base))

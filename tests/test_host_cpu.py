@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(_lib.lib, name), name
     assert declared - {"md_last_error", "md_abi_version"} == set(_lib.SIGNATURES)
-    assert _lib.lib.md_abi_version() == 1
+    assert _lib.lib.md_abi_version() == 2
     assert _lib.lib.md_last_error() is not None
 
 
@@ -117,3 +117,21 @@ def test_world_size_2_sharding_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_custom_ops_are_registered_for_cuda_only():
+    """BASELINE.json north star: the kernels are exposed as PyTorch custom ops (`torch.ops.musediff.*`) — registered for the
+    CUDA dispatch key and nothing else, so a CPU tensor can never take a fallback path."""
+    import torch
+    from musediffusion_b200 import _lib, custom_ops
+    for name in custom_ops.OP_NAMES:
+        op = getattr(torch.ops.musediff, name)
+        assert "musediff::" + name in str(op.default._schema)
+    # every kernel entry of the header has its op (md_set_schedule is a host->device table copy, the padded-vocab helper is host only)
+    entries = set(_lib.SIGNATURES) - {"md_set_schedule", "md_round_tc_padded_vocab"}
+    assert {"md_" + n for n in custom_ops.OP_NAMES} == entries
+    with pytest.raises(NotImplementedError):
+        torch.ops.musediff.cast_f32_bf16(torch.ones(4), torch.empty(4, dtype=torch.bfloat16))
+    with pytest.raises(_lib.MuseDiffLibraryError):
+        from musediffusion_b200 import ops
+        ops.cast_bf16(torch.ones(4))
