@@ -61,7 +61,10 @@ static SchedRef sched_ref() {
 // Philox4x32-10 + inverse-CDF normals
 // ----------------------------------------------------------------------------------------------
 // Acklam's rational approximation of the standard normal quantile (|rel err| ~1e-9 in exact arithmetic); general path.
-MD_DEVINL float norm_quantile(float p) {
+// Takes q = p - 0.5 in (-0.5, 0.5): the tails are evaluated from 0.5 - |q| (exact in fp32: a Sterbenz subtraction), never
+// from p = q + 0.5, which rounds to exactly 1.0 for the topmost 24-bit draw and would turn it into a +11.5 sigma outlier;
+// both tails now bottom out symmetrically at |n| = 5.42 (p = 2^-25).
+MD_DEVINL float norm_quantile_q(float q) {
     const float a0 = -3.969683028665376e+01f, a1 = 2.209460984245205e+02f, a2 = -2.759285104469687e+02f,
                 a3 = 1.383577518672690e+02f, a4 = -3.066479806614716e+01f, a5 = 2.506628277459239e+00f;
     const float b0 = -5.447609879822406e+01f, b1 = 1.615858368580409e+02f, b2 = -1.556989798598866e+02f,
@@ -71,15 +74,13 @@ MD_DEVINL float norm_quantile(float p) {
     const float d0 = 7.784695709041462e-03f, d1 = 3.224671290700398e-01f, d2 = 2.445134137142996e+00f,
                 d3 = 3.754408661907416e+00f;
     const float plow = 0.02425f;
-    if (p < plow || p > 1.0f - plow) {
-        const bool upper = p > 0.5f;
-        const float pp = upper ? 1.0f - p : p;
-        const float q = sqrtf(-2.0f * logf(fmaxf(pp, 1e-30f)));
-        const float x = __fdividef((((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5),
-                                   ((((d0 * q + d1) * q + d2) * q + d3) * q + 1.0f));
-        return upper ? -x : x;
+    const float pp = 0.5f - fabsf(q);                     // tail probability on the side of q
+    if (pp < plow) {
+        const float r = sqrtf(-2.0f * logf(fmaxf(pp, 1e-30f)));
+        const float x = __fdividef((((((c0 * r + c1) * r + c2) * r + c3) * r + c4) * r + c5),
+                                   ((((d0 * r + d1) * r + d2) * r + d3) * r + 1.0f));      // negative: lower-tail quantile
+        return q > 0.0f ? -x : x;
     }
-    const float q = p - 0.5f;
     const float r = q * q;
     return __fdividef((((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q,
                       (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1.0f));
@@ -133,7 +134,7 @@ struct NoiseGen {
     template <bool kCentral>
     MD_DEVINL float one(uint32_t bits) const {
         const float q = fmaf((float)(bits >> 8), q_scale, q_bias);
-        return kCentral ? norm_quantile_central(q) : norm_quantile(q + 0.5f);
+        return kCentral ? norm_quantile_central(q) : norm_quantile_q(q);
     }
     // four normals for the aligned group of 4 elements starting at global element index 4*g
     template <bool kCentral>

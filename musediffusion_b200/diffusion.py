@@ -324,7 +324,8 @@ class GaussianDiffusion:
             indices = idx_list
 
         def rounds_at(i):
-            """clamp gating, diffusion.py:517-526 (the DDIM loop always rounds, :889-899)"""
+            """clamp gating, diffusion.py:517-526 (the DDIM loop always rounds, :889-899); like the reference, the DDPM loop
+            raises TypeError when clamp_step is left at its default None"""
             if mode != _lib.STEP_DDPM:
                 return True
             return (i >= clamp_step) if clamp_first else not (i > clamp_step)
@@ -418,8 +419,7 @@ class GaussianDiffusion:
         indices = list(range(self.num_timesteps))[::-1][slice(t_enc)]
         final, last = [], None
         for last in self._loop(_lib.STEP_DDPM, model, shape, noise, clip_denoised, denoised_fn, model_kwargs, device,
-                               progress, top_p, clamp_step if clamp_step is not None else 0, clamp_first, mask, x_start,
-                               eta, indices, want_aux=False):
+                               progress, top_p, clamp_step, clamp_first, mask, x_start, eta, indices, want_aux=False):
             if not only_last:
                 final.append(last[0].clone())
         if only_last:
@@ -434,9 +434,8 @@ class GaussianDiffusion:
         """diffusion.py:475-540: generator of p_sample dicts."""
         indices = list(range(self.num_timesteps))[::-1][slice(t_enc)]
         for sample, pred, mean, t in self._loop(_lib.STEP_DDPM, model, shape, noise, clip_denoised, denoised_fn,
-                                                model_kwargs, device, progress, top_p,
-                                                clamp_step if clamp_step is not None else 0, clamp_first, mask, x_start,
-                                                eta, indices, want_aux=True):
+                                                model_kwargs, device, progress, top_p, clamp_step, clamp_first, mask,
+                                                x_start, eta, indices, want_aux=True):
             yield {"sample": sample, "pred_xstart": pred, "greedy_mean": mean,
                    "out": {"mean": mean, "pred_xstart": pred,
                            "variance": _extract_into_tensor(self.model_variance, t.long(), sample.shape),

@@ -49,6 +49,12 @@ def broadcast_model(model, src=0):
     with torch.no_grad():
         for p in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(p.data, src)
+    # writes through `.data` do not bump the tensors' version counters, which key the packed bf16 weights and the split
+    # embedding: rebuild them explicitly so that no rank keeps serving its pre-broadcast weights
+    from . import ops
+    ops._split_cache.clear()
+    if hasattr(model, "weight_pack") and next(model.parameters()).is_cuda:
+        model.weight_pack(force=True)
 
 
 def all_gather_tokens(tokens):

@@ -16,6 +16,8 @@ def seed_all(seed, deterministic=False):
     if isinstance(seed, int):
         seed = hash(seed)
     random.seed(seed)
+    from .corruption import generator                       # initialization.py:15,26: the corruptions' own stream
+    generator.seed(seed)
     np.random.seed(seed % (2 ** 32))
     torch.manual_seed(seed)
     if torch.cuda.is_available():

@@ -67,43 +67,32 @@ class _Encoder(nn.Module):
 
 
 class WeightPack:
-    """Device-resident bf16 / fp32 weights in the layout the kernels consume (built once per parameter version)."""
+    """Device-resident bf16 / fp32 weights in the layout the kernels consume: built from the parameters once per parameter
+    version (`checkpoint.pack_tensors`), or served straight from a packed weight file (`checkpoint.load_pack`)."""
 
-    def __init__(self, model):
-        dev = model.word_embedding.weight.device
+    def __init__(self, model, tensors=None):
+        dev = model.word_embedding.weight.device if tensors is None else tensors["E"].device
         if dev.type != "cuda":
             raise _lib.MuseDiffLibraryError("TransformerNetModel.forward needs the model on a CUDA device "
                                             "(there is no CPU path); call model.to('cuda') first")
-        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
-        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        if tensors is None:
+            from .checkpoint import pack_tensors
+            tensors = pack_tensors({k: v for k, v in model.state_dict().items()}, model.num_heads)
         self.device = dev
         self.H = model.hidden_size
         self.NH = model.num_heads
         self.eps = model.layer_norm_eps
-        self.E = f32(model.word_embedding.weight)
-        self.lm_bias = f32(model.lm_head.bias)
-        self.t0_w, self.t0_b = f32(model.time_embed[0].weight), f32(model.time_embed[0].bias)
-        self.t2_w, self.t2_b = f32(model.time_embed[2].weight), f32(model.time_embed[2].bias)
-        self.up1_w, self.up1_b = bf(model.input_up_proj[0].weight), f32(model.input_up_proj[0].bias)
-        self.up2_w, self.up2_b = bf(model.input_up_proj[2].weight), f32(model.input_up_proj[2].bias)
-        self.pos = f32(model.position_embeddings.weight)
-        self.ln_g, self.ln_b = f32(model.LayerNorm.weight), f32(model.LayerNorm.bias)
-        self.dn1_w, self.dn1_b = bf(model.output_down_proj[0].weight), f32(model.output_down_proj[0].bias)
-        self.dn2_w, self.dn2_b = bf(model.output_down_proj[2].weight), f32(model.output_down_proj[2].bias)
-        scale = 1.0 / math.sqrt(self.H // self.NH)     # exact power of two for head dim 64: folding it into W_q is lossless
+        for name in ("E", "lm_bias", "t0_w", "t0_b", "t2_w", "t2_b", "up1_w", "up1_b", "up2_w", "up2_b", "pos", "ln_g", "ln_b",
+                     "dn1_w", "dn1_b", "dn2_w", "dn2_b"):
+            setattr(self, name, tensors[name])
         self.layers = []
-        for lyr in model.input_transformers.layer:
-            sa = lyr.attention.self
-            wqkv = torch.cat([sa.query.weight.detach().float() * scale, sa.key.weight.detach().float(),
-                              sa.value.weight.detach().float()], dim=0)
-            bqkv = torch.cat([sa.query.bias.detach().float() * scale, sa.key.bias.detach().float(),
-                              sa.value.bias.detach().float()], dim=0)
-            ao, ff = lyr.attention.output, lyr.output
-            self.layers.append(SimpleNamespace(
-                wqkv=bf(wqkv), bqkv=f32(bqkv),
-                wo=bf(ao.dense.weight), bo=f32(ao.dense.bias), g1=f32(ao.LayerNorm.weight), b1=f32(ao.LayerNorm.bias),
-                w1=bf(lyr.intermediate.dense.weight), bi=f32(lyr.intermediate.dense.bias),
-                w2=bf(ff.dense.weight), b2=f32(ff.dense.bias), g2=f32(ff.LayerNorm.weight), b2n=f32(ff.LayerNorm.bias)))
+        i = 0
+        while "l%d.wqkv" % i in tensors:
+            self.layers.append(SimpleNamespace(**{k: tensors["l%d.%s" % (i, k)] for k in
+                                                  ("wqkv", "bqkv", "wo", "bo", "g1", "b1", "w1", "bi", "w2", "b2", "g2", "b2n")}))
+            i += 1
+        if i != len(model.input_transformers.layer):
+            raise ValueError("weight pack holds %d encoder layers, the model has %d" % (i, len(model.input_transformers.layer)))
         # split-bf16 operands for fp32-grade logits on the tensor cores (get_logits):
         #   x.E^T = [xh|xl|xh|xl] . [Eh|Eh|El|El]^T   (all four partial products, K = 4 D, fp32 accumulation)
         V, D = self.E.shape
@@ -182,6 +171,31 @@ class TransformerNetModel(nn.Module):
     # ------------------------------------------------------------------------------------------ packing
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def load_weight_pack(self, path, device=None):
+        """Serve the kernels from a packed weight file (checkpoint.write_pack) instead of the nn.Parameters: one read of the
+        file into one device buffer, no fp32 state dict, no per-tensor packing kernels.  The parameters the rest of the
+        sampling path touches directly (word_embedding / lm_head.bias, run/sample.py:92-101 clones the embedding) are
+        filled from the pack and the module is moved to `device`; the encoder's nn.Parameters keep their construction-
+        time values and are NOT what forward() computes with until `load_state_dict` / `weight_pack(force=True)` is called."""
+        from .checkpoint import load_pack
+        device = torch.device(device if device is not None else "cuda")
+        config, tensors = load_pack(path, device)
+        for k, mine in (("hidden_size", self.hidden_size), ("num_attention_heads", self.num_heads),
+                        ("num_hidden_layers", len(self.input_transformers.layer)), ("hidden_dim", self.input_dims),
+                        ("seq_len", self.config.max_position_embeddings), ("vocab_size", self.config.vocab_size)):
+            if k in config and int(config[k]) != int(mine):
+                raise ValueError("weight pack %s was written for %s=%s, this model has %s" % (path, k, config[k], mine))
+        self.to(device)
+        with torch.no_grad():
+            self.word_embedding.weight.copy_(tensors["E"])
+            self.lm_head.bias.copy_(tensors["lm_bias"])
+            self.position_embeddings.weight.copy_(tensors["pos"])
+        self._pack = WeightPack(self, tensors=tensors)
+        self._pack_key = self._params_key()
+        self._pack_refs = [p.data for p in self.parameters()]
+        self._ws = {}
+        return self
 
     def weight_pack(self, force=False):
         key = self._params_key()

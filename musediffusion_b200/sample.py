@@ -66,14 +66,43 @@ def sample_batch(model, diffusion, model_emb, cond, mode, step, diffusion_steps,
 
 
 def load_training_args(model_path):
-    """config/sample.py:114-134: `training_args.json` sits next to the checkpoint."""
-    with open(os.path.join(os.path.dirname(os.path.abspath(model_path)), "training_args.json")) as f:
-        return SimpleNamespace(**json.load(f))
+    """config/sample.py:114-134: `training_args.json` (the reference's `TrainSettings(...).json()`) sits next to the checkpoint."""
+    from .checkpoint import load_training_args as _load
+    return _load(model_path)
+
+
+def load_model(model_path, device):
+    """run/sample.py:76-88: model + diffusion from a model directory.  `model_path` is either the reference's `model_*.pt`
+    (state dict; `training_args.json` next to it) or a packed weight file `*.mdpack` written by `python -m
+    musediffusion_b200 pack` (its header carries the model configuration, so training_args.json is optional)."""
+    from . import checkpoint
+    if model_path.endswith(".mdpack"):
+        header, _ = checkpoint.read_pack_header(model_path)
+        cfg = header["config"]
+        targs_path = checkpoint.training_args_path(model_path)
+        targs = checkpoint.load_training_args(targs_path) if os.path.isfile(targs_path) else SimpleNamespace(**checkpoint.MODEL_FIELDS)
+        for k in checkpoint.MODEL_FIELDS:
+            if k in cfg:
+                setattr(targs, k, cfg[k])
+        targs.encoder_config = {k: cfg[k] for k in ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size",
+                                                     "layer_norm_eps") if k in cfg}
+        model, diffusion = create_model_and_diffusion(targs)
+        model.eval().requires_grad_(False)
+        model.load_weight_pack(model_path, device)
+    else:
+        targs = load_training_args(model_path)
+        model, diffusion = create_model_and_diffusion(targs)
+        model.load_state_dict(checkpoint.load_state_dict(model_path, map_location="cpu"))
+        model.eval().requires_grad_(False).to(device)
+    return model, diffusion, targs
 
 
 def create_parser():
     p = argparse.ArgumentParser(prog="python -m musediffusion_b200")
     sub = p.add_subparsers(dest="mode", required=True)
+    pk = sub.add_parser("pack", help="write a packed bf16 weight file (*.mdpack) from a reference checkpoint")
+    pk.add_argument("--model_path", required=True, help="model_*.pt written by the reference's trainer")
+    pk.add_argument("--out", default=None, help="output path (default: <model_path minus .pt>.mdpack)")
     for name in ("generation", "modification"):
         sp = sub.add_parser(name)
         sp.add_argument("--model_path", required=True)
@@ -95,14 +124,28 @@ def create_parser():
     return p
 
 
+def pack_main(args):
+    """`python -m musediffusion_b200 pack --model_path model_000000.pt`: checkpoint -> packed weight file (host only)."""
+    from . import checkpoint
+    targs = load_training_args(args.model_path)
+    model, _ = create_model_and_diffusion(targs)
+    sd = checkpoint.load_state_dict(args.model_path, map_location="cpu")
+    missing = set(model.state_dict()) - set(sd)
+    if missing:
+        raise KeyError("checkpoint lacks %d keys, e.g. %s" % (len(missing), sorted(missing)[:3]))
+    out = args.out or (args.model_path[:-3] if args.model_path.endswith(".pt") else args.model_path) + ".mdpack"
+    checkpoint.write_pack(out, sd, checkpoint.model_config_of(targs, model))
+    print("### wrote %s (%.1f MB)" % (out, os.path.getsize(out) / 1e6))
+    return out
+
+
 def main(argv=None):
     args = create_parser().parse_args(argv)
+    if args.mode == "pack":
+        return pack_main(args)
     from . import decode_util, dist
     rank, world, dev = dist.setup()
-    targs = load_training_args(args.model_path)
-    model, diffusion = create_model_and_diffusion(targs)
-    model.load_state_dict(torch.load(args.model_path, map_location="cpu"))
-    model.eval().requires_grad_(False).to(dev)
+    model, diffusion, targs = load_model(args.model_path, dev)
     model_emb = build_model_emb(model, dev)
     seed_all(args.sample_seed, deterministic=True)
     if args.input_npz:

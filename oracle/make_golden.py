@@ -240,6 +240,52 @@ def golden_loop_base(fname, mode, B, seed, diffusion_steps, step, strength=1.0, 
     print(fname, tokens.shape, len(rec_ids), "rounding calls, %.0f s" % (time.time() - t0), tokens[0, :20].tolist())
 
 
+def corruption_cases(n=40, L=320, seed=4):
+    """rows shaped like the modification pipeline's input (`[meta .. EOS notes .. EOS pad]`, data/preprocess.py:50-56)."""
+    rows, r = [], 0
+    while len(rows) < n:
+        row = O.make_synthetic_batch("modification", 1, L, seed=seed * 100 + r)["input_ids"][0].astype(np.int64)
+        r += 1
+        bars, eos = np.flatnonzero(row == 2), np.flatnonzero(row == 1)
+        if len(bars) >= 3 and eos[-1] > bars[-1]:   # random_rotating asserts >= 2 bars and cuts the last bar at the final EOS
+            rows.append(row)
+    return np.stack(rows)
+
+
+def golden_corruption():
+    """the reference's own Corruptions (data/corruption.py) on 40 rows, one seeded stream:
+    each single corruption, the default config `mt,mn,rn,rr` / corr_max 4 / corr_p 0.5, and a config with kwargs."""
+    import torch
+    from MuseDiffusion.data import corruption as RC
+    rows = corruption_cases()
+    out = {"rows": rows}
+    configs = {"mt": ("mt", 1, 1.0, None), "mn": ("mn", 1, 1.0, None), "rn": ("rn", 1, 1.0, None), "rr": ("rr", 1, 1.0, None),
+               "default": ("mt,mn,rn,rr", 4, 0.5, None), "kw": ("rr,mt,rn", 2, 0.7, "dict(p=0.15, count=2)")}
+    for tag, (avail, cmax, p, kw) in configs.items():
+        corr = RC.Corruptions.from_config(avail, cmax, p, kw)
+        RC.generator.seed(1234)
+        res = [corr(torch.from_numpy(r)).numpy() for r in rows]
+        # a rotation after a masked final EOS changes the row length (corruption.py:185-193): store padded with -1 + lengths
+        width = max(len(x) for x in res)
+        out[tag] = np.stack([np.concatenate([x, np.full(width - len(x), -1, np.int64)]) for x in res])
+        out[tag + "_len"] = np.array([len(x) for x in res], np.int64)
+        out[tag + "_next"] = np.float64(RC.generator.random())          # the stream position afterwards
+    np.savez_compressed(os.path.join(OUT, "corruption.npz"), **out)
+    print("corruption.npz", {k: (int(out[k + "_len"].min()), int(out[k + "_len"].max())) for k in configs})
+
+
+def golden_training_args():
+    """`training_args.json` exactly as the reference's trainer writes it
+    (`TrainSettings(...).json()`, pydantic v1; config/train.py:101-124) — defaults, and one with non-default model fields."""
+    from MuseDiffusion.config import TrainSettings
+    with open(os.path.join(OUT, "training_args_default.json"), "w") as f:
+        f.write(TrainSettings().json())
+    with open(os.path.join(OUT, "training_args_small.json"), "w") as f:
+        f.write(TrainSettings(seq_len=256, diffusion_steps=400, noise_schedule="cosine", predict_xstart=False,
+                              rescale_timesteps=False, timestep_respacing="ddim50", use_corruption=False).json())
+    print("training_args_*.json")
+
+
 def golden_meta_prefix():
     """README example meta -> 27-token prefix through the real MetaToSequence."""
     from MuseDiffusion.utils.decode_util import meta_to_batch
@@ -339,6 +385,12 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "merge":
         golden_merge_and_mask()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "corruption":
+        golden_corruption()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "args":
+        golden_training_args()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "loops":
         import torch
         torch.manual_seed(0)
@@ -374,6 +426,8 @@ def main():
     golden_decode_prepare()
     golden_merge_and_mask()
     golden_metrics()
+    golden_training_args()
+    golden_corruption()
 
 
 if __name__ == "__main__":
