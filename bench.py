@@ -361,13 +361,17 @@ def sample_generation_steps(model, diffusion, model_emb, cond, k_steps, dev):
 
 
 def ncu_traffic(kernel, B):
-    """dram bytes (read + write) per launch from the committed `ncu --set full` capture (profiles/r1_traffic.json holds
-    bytes per sequence measured at 64 sequences); null when no capture exists for this kernel."""
+    """dram bytes (read + write) per launch from the committed `ncu --set full` capture of this kernel
+    (profiles/r2_traffic.json, written by tools/summarize_profiles.py from tools/ncu_round.sh's reports: bytes of ONE launch at
+    the captured batch, scaled linearly to B); null when no capture exists for this kernel."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        key = kernel.split(":")[0]
-        return float(t[key]["dram_bytes_per_sequence"]) * B if key in t else None
+        ent = t.get(kernel) or t.get(kernel.split(":")[0])
+        if ent is None and ":" in kernel:                      # same GEMM shape captured at another batch: match on N x K + epilogue
+            tail = kernel.split("x", 1)[1]
+            ent = next((v for k, v in t.items() if ":" in k and k.split("x", 1)[1] == tail), None)
+        return float(ent["dram_bytes_per_launch"]) * B / float(ent["batch"]) if ent else None
     except Exception:
         return None
 

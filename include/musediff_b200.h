@@ -87,6 +87,12 @@ int md_round_argmin(const float* x, const float* E, int32_t* idx, float* margin,
 int md_logits_argmax(const float* x, const float* E, const float* bias, int32_t* tok, float* margin, int64_t M, int V,
                      int D, cudaStream_t stream);
 
+/* get_logits with logits_mode = 2 (models/network.py:94-104): scores[m, v] = -sqrt(clamp(|E_v|^2 + |x_m|^2 - 2 x_m.E_v, 0)).
+ * dot fp32 [M, dot_stride] holds x_m.E_v (from the split-bf16 md_linear_bf16 contraction), esq fp32 [V] = |E_v|^2
+ * (md_embed_split), x fp32 [M, D]; out fp32 [M, V]. */
+int md_dist_scores(const float* x, const float* dot, const float* esq, float* out, int64_t M, int V, int dot_stride, int D,
+                   cudaStream_t stream);
+
 /* Tensor-core versions of the two reductions above (tcgen05, split-bf16 operands x = xh + xl, E = Eh + El with the four
  * partial products accumulated in fp32: fp32-grade scores, the score matrix stays in TMEM).
  *   md_embed_split: once per embedding matrix.  E2 = bf16 [Vp, 2D] = [Eh | El], sqnorm = fp32 [Vp] = |E_v|^2 (+inf on
@@ -112,7 +118,7 @@ int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x
  *   DDIM: eps = (sr[t] x_t - pred)/srm1[t]; sigma = eta sqrt((1-abp)/(1-ab)) sqrt(1-ab/abp);
  *         x' = pred sqrt(abp) + sqrt(1-abp-sigma^2) eps + [t != 0] sigma n
  *   x'   = mask == 0 ? x_start : x'                     (diffusion.py:394-397, 752-755)
- * n = noise[m, d] if noise != NULL, else a counter-based Philox4x32-10 normal keyed by (seed, step_counter, global
+ * n = noise[m, d] if noise != NULL, else a counter-based Philox4x32-7 normal keyed by (seed, step_counter, global
  * element index (seq_offset*L + m)*D + d), truncated to |n| <= top_p by inverse-CDF when top_p > 0 (the law the
  * reference's rejection loop :378-385 samples).  t: int32 schedule index, t[b * t_stride] (t_stride 1 = per sequence,
  * 0 = one value for the batch, as inside the loops :516,887).  mask: int32, indexed m*mask_tok_stride + d*mask_d_stride

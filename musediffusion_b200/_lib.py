@@ -26,6 +26,7 @@ SIGNATURES = {
     "md_round_argmin": [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
     "md_logits_argmax": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p],
     "md_split_bf16": [c_p, c_p, c_i64, c_i, c_i, c_p],
+    "md_dist_scores": [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_p],
     "md_round_tc_padded_vocab": [c_i],
     "md_embed_split": [c_p, c_i, c_i, c_p, c_p, c_p],
     "md_round_argmin_tc": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_p],

@@ -58,12 +58,17 @@ static SchedRef sched_ref() {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Philox4x32-10 + inverse-CDF normals
+// Philox4x32-7 + inverse-CDF normals.  Seven rounds are the fewest that pass BigCrush (Salmon et al., SC'11, table 2;
+// ten is the library default); each round is two 32x32->64 multiplies and two three-input XORs for four outputs.
+// A normal costs: its share of the cipher (7 instructions), one LOP3 + one FFMA to turn 23 random bits into
+// q = p - 0.5 (mantissa trick, no I2F — conversions run on the 16-lane XU pipe), and the quantile polynomial evaluated
+// for two values per instruction (packed f32x2).
 // ----------------------------------------------------------------------------------------------
+constexpr int kPhiloxRounds = 7;
 // Acklam's rational approximation of the standard normal quantile (|rel err| ~1e-9 in exact arithmetic); general path.
 // Takes q = p - 0.5 in (-0.5, 0.5): the tails are evaluated from 0.5 - |q| (exact in fp32: a Sterbenz subtraction), never
-// from p = q + 0.5, which rounds to exactly 1.0 for the topmost 24-bit draw and would turn it into a +11.5 sigma outlier;
-// both tails now bottom out symmetrically at |n| = 5.42 (p = 2^-25).
+// from p = q + 0.5, which rounds to exactly 1.0 for the topmost draw and would turn it into a +11.5 sigma outlier;
+// both tails bottom out symmetrically at |n| = 5.30 (p = 2^-24).
 MD_DEVINL float norm_quantile_q(float q) {
     const float a0 = -3.969683028665376e+01f, a1 = 2.209460984245205e+02f, a2 = -2.759285104469687e+02f,
                 a3 = 1.383577518672690e+02f, a4 = -3.066479806614716e+01f, a5 = 2.506628277459239e+00f;
@@ -97,14 +102,24 @@ MD_DEVINL float norm_quantile_central(float q) {
     p = fmaf(p, r, 2.506624698638916f);
     return p * q;
 }
+// the same polynomial for two values per instruction (packed f32x2: 7 issue slots per pair)
+MD_DEVINL uint64_t norm_quantile_central_x2(uint64_t q) {
+    const uint64_t r = f2_mul(q, q);
+    uint64_t p = f2_fma(f2_pack(643.067138671875f, 643.067138671875f), r, f2_pack(-38.967872619628906f, -38.967872619628906f));
+    p = f2_fma(p, r, f2_pack(21.74688720703125f, 21.74688720703125f));
+    p = f2_fma(p, r, f2_pack(5.587021827697754f, 5.587021827697754f));
+    p = f2_fma(p, r, f2_pack(2.6269679069519043f, 2.6269679069519043f));
+    p = f2_fma(p, r, f2_pack(2.506624698638916f, 2.506624698638916f));
+    return f2_mul(p, q);
+}
 struct NoiseGen {
-    uint32_t kx[10], ky[10];   // Philox round keys (key + round * Weyl constants), precomputed on the host
+    uint32_t kx[kPhiloxRounds], ky[kPhiloxRounds];   // Philox round keys (key + round * Weyl constants), precomputed on the host
     uint32_t step_lo, step_hi;
-    float q_scale, q_bias;     // q = p - 0.5 = (top 24 random bits) * q_scale + q_bias
+    float q_scale, q_bias;     // q = p - 0.5 = (m - 1.5) * q_scale + q_bias, m = 1.f + (top 23 random bits) * 2^-23 (mantissa trick)
     int central;               // 1: |q| <= 0.3414 guaranteed -> polynomial quantile
     __host__ void init(uint64_t seed, uint64_t step, float top_p) {
         uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < kPhiloxRounds; ++r) {
             kx[r] = k0;
             ky[r] = k1;
             k0 += 0x9E3779B9u;
@@ -117,30 +132,36 @@ struct NoiseGen {
             lo = 0.5 * erfc((double)top_p / sqrt(2.0));  // Phi(-top_p)
             span = 1.0 - 2.0 * lo;
         }
-        // u = (bits24 + 0.5) * 2^-24 in (0, 1);  p = lo + u * span;  q = p - 0.5
-        q_scale = (float)(span * 5.9604644775390625e-08);
-        q_bias = (float)(lo - 0.5 + 0.5 * span * 5.9604644775390625e-08);
+        // m = 1 + bits23 * 2^-23 in [1, 2);  u = (m - 1) + 2^-24 in (0, 1);  p = lo + u * span;
+        // q = p - 0.5 = (m - 1.5) * span + (lo - 0.5 + 0.5 span) + span 2^-24, and lo - 0.5 + 0.5 span = 0 (symmetric band).
+        // m - 1.5 is exact in fp32, so the two tails end at exactly -0.5 + 2^-24 and 0.5 - 2^-24 (|n| <= 5.30 untruncated)
+        q_scale = (float)span;
+        q_bias = (float)((lo - 0.5 + 0.5 * span) + span * 5.9604644775390625e-08);
         central = (top_p > 0.0f && top_p <= 1.0f) ? 1 : 0;
     }
     MD_DEVINL uint4 philox(uint4 c) const {
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < kPhiloxRounds; ++r) {
             const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;     // one IMAD.WIDE gives hi and lo
             const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
             c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ kx[r], (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ ky[r], (uint32_t)p0);
         }
         return c;
     }
-    template <bool kCentral>
-    MD_DEVINL float one(uint32_t bits) const {
-        const float q = fmaf((float)(bits >> 8), q_scale, q_bias);
-        return kCentral ? norm_quantile_central(q) : norm_quantile_q(q);
+    MD_DEVINL float q_of(uint32_t bits) const {                 // 23 random bits -> q = p - 0.5: LOP3 + FADD + FFMA, no I2F
+        return fmaf(__fadd_rn(__uint_as_float(0x3f800000u | (bits >> 9)), -1.5f), q_scale, q_bias);
     }
     // four normals for the aligned group of 4 elements starting at global element index 4*g
     template <bool kCentral>
     MD_DEVINL float4 draw4t(uint64_t g, uint32_t slo, uint32_t shi) const {      // step counter supplied by the caller
         const uint4 r = philox(make_uint4((uint32_t)g, (uint32_t)(g >> 32), slo, shi));
-        return make_float4(one<kCentral>(r.x), one<kCentral>(r.y), one<kCentral>(r.z), one<kCentral>(r.w));
+        if (kCentral) {
+            float4 o;
+            f2_unpack(norm_quantile_central_x2(f2_pack(q_of(r.x), q_of(r.y))), o.x, o.y);
+            f2_unpack(norm_quantile_central_x2(f2_pack(q_of(r.z), q_of(r.w))), o.z, o.w);
+            return o;
+        }
+        return make_float4(norm_quantile_q(q_of(r.x)), norm_quantile_q(q_of(r.y)), norm_quantile_q(q_of(r.z)), norm_quantile_q(q_of(r.w)));
     }
     template <bool kCentral>
     MD_DEVINL float4 draw4t(uint64_t g) const { return draw4t<kCentral>(g, step_lo, step_hi); }
@@ -653,6 +674,25 @@ __global__ void __launch_bounds__(256) timestep_out_kernel(const float* __restri
     }
 }
 
+// get_logits, logits_mode 2 (network.py:94-104): scores[m, v] = -sqrt(clamp(|E_v|^2 + |x_m|^2 - 2 x_m.E_v, 0)); the dot products
+// come from the split-bf16 tensor-core GEMM, |E_v|^2 from md_embed_split.  One warp per row: |x_m|^2 by shuffle reduction.
+__global__ void __launch_bounds__(256) dist_scores_kernel(const float* __restrict__ x, const float* __restrict__ dot, const float* __restrict__ esq,
+                                                          float* __restrict__ out, int64_t M, int V, int dot_stride, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = warp_global; m < M; m += nwarps) {
+        float q = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = x[m * D + d]; q = fmaf(v, v, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        for (int v = lane; v < V; v += 32) {
+            const float d2 = __fsub_rn(__fadd_rn(esq[v], q), __fmul_rn(2.0f, dot[m * dot_stride + v]));
+            out[m * V + v] = -sqrtf(fmaxf(d2, 0.0f));
+        }
+    }
+}
+
 static int ew_grid(int64_t work_items, int threads) {
     const int64_t blocks = (work_items + threads - 1) / threads;
     const int64_t cap = (int64_t)num_sms() * 8;   // 8 resident 256-thread CTAs per SM, grid-stride beyond that
@@ -711,6 +751,14 @@ extern "C" __attribute__((visibility("default"))) int md_set_schedule(const floa
                 return MD_ERR_CUDA;
     }
     return check_cuda(cudaStreamSynchronize(stream), "md_set_schedule sync");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_dist_scores(const float* x, const float* dot, const float* esq, float* out, int64_t M, int V,
+                              int dot_stride, int D, cudaStream_t stream) {
+    if (M == 0) return MD_OK;
+    if (V <= 0 || D <= 0 || dot_stride < V) { set_last_error("md_dist_scores: bad sizes V=%d D=%d stride=%d", V, D, dot_stride); return MD_ERR_ARG; }
+    dist_scores_kernel<<<ew_grid(M * 32, 256), 256, 0, stream>>>(x, dot, esq, out, M, V, dot_stride, D);
+    return check_cuda(cudaGetLastError(), "dist_scores launch");
 }
 
 extern "C" __attribute__((visibility("default"))) int md_cast_f32_bf16(const float* in, void* out, int64_t n, cudaStream_t stream) {

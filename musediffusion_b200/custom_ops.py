@@ -99,6 +99,10 @@ def _split_bf16(x, out, copies):
     launch("md_split_bf16", _p(x), _p(out), x.numel() // D, D, copies, _stream())
 
 
+def _dist_scores(x, dot, esq, out):
+    launch("md_dist_scores", _p(x), _p(dot), _p(esq), _p(out), out.shape[0], out.shape[1], dot.shape[1], x.shape[-1], _stream())
+
+
 def _embed_split(E, E2, sqnorm):
     launch("md_embed_split", _p(E), E.shape[0], E.shape[1], _p(E2), _p(sqnorm), _stream())
 
@@ -170,6 +174,7 @@ _define("round_argmin(Tensor x, Tensor E, Tensor(a!) idx, Tensor(b!)? margin) ->
 _define("logits_argmax(Tensor x, Tensor E, Tensor bias, Tensor(a!) tok, Tensor(b!)? margin) -> ()", _logits_argmax)
 _define("split_bf16(Tensor x, Tensor(a!) out, int copies) -> ()", _split_bf16)
 _define("embed_split(Tensor E, Tensor(a!) E2, Tensor(b!) sqnorm) -> ()", _embed_split)
+_define("dist_scores(Tensor x, Tensor dot, Tensor esq, Tensor(a!) out) -> ()", _dist_scores)
 _define("round_argmin_tc(Tensor x, Tensor E2, Tensor cst, Tensor(a!) ws, Tensor(b!) idx, Tensor(c!)? margin, int V, int mode) -> ()",
         _round_argmin_tc)
 _define("posterior_step(Tensor x_t, Tensor? idx, Tensor? pred, Tensor? E, Tensor? noise, int seed, int step_counter, int seq_offset, "
@@ -191,6 +196,6 @@ _define("sequence_metrics(Tensor notes, Tensor note_len, Tensor meta, Tensor(a!)
 _define("onnc(Tensor vectors, Tensor(a!)? msim, Tensor(b!) most_sim) -> ()", _onnc)
 
 OP_NAMES = ["cast_f32_bf16", "embed_gather", "timestep_mlp", "layernorm_bf16", "linear_bf16", "attention_bf16", "round_argmin",
-            "logits_argmax", "split_bf16", "embed_split", "round_argmin_tc", "posterior_step", "xstart_from_eps", "q_sample",
+            "logits_argmax", "split_bf16", "dist_scores", "embed_split", "round_argmin_tc", "posterior_step", "xstart_from_eps", "q_sample",
             "fill_normal", "step_advance", "decode_prepare", "merge_and_mask", "sequence_metrics", "onnc"]
 ops = getattr(torch.ops, NAMESPACE)

@@ -271,11 +271,22 @@ class GaussianDiffusion:
 
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0,
                     langevin_fn=None, mask=None, x_start=None):
-        """diffusion.py:701-757."""
-        if langevin_fn:
-            raise NotImplementedError("langevin_fn is not used by the sampling path")
-        sample, pred, _ = self._step(_lib.STEP_DDIM, model, x, t, clip_denoised, denoised_fn, model_kwargs, None, mask,
-                                     x_start, eta)
+        """diffusion.py:701-757.  `langevin_fn(sample, mean_pred, sigma, alpha_bar_prev[t[0]], t, x)` (:748-750) is applied
+        to the un-masked sample; the mask select that follows it (:752-755) is md_q_sample's `mask == 0 ? x_start : sample`."""
+        if not langevin_fn:
+            sample, pred, _ = self._step(_lib.STEP_DDIM, model, x, t, clip_denoised, denoised_fn, model_kwargs, None, mask,
+                                         x_start, eta)
+            return {"sample": sample, "pred_xstart": pred}
+        sample, pred, mean_pred = self._step(_lib.STEP_DDIM, model, x, t, clip_denoised, denoised_fn, model_kwargs, None, None,
+                                             None, eta)
+        tt = t.reshape(-1).long()
+        ab, abp = self.alphas_cumprod, self.alphas_cumprod_prev
+        sigma_tab = eta * np.sqrt((1 - abp) / (1 - ab)) * np.sqrt(1 - ab / abp)
+        sigma = _extract_into_tensor(sigma_tab, tt if tt.numel() == x.shape[0] else tt.expand(x.shape[0]), x.shape)
+        sample = langevin_fn(sample, mean_pred, sigma, self.alphas_cumprod_prev[int(tt[0])], t, x)
+        if mask is not None:
+            sample = ops.q_sample(sample.new_empty(0) if x_start is None else x_start.to(torch.float32).contiguous(), None,
+                                  noise=sample.to(torch.float32).contiguous(), mask=mask)
         return {"sample": sample, "pred_xstart": pred}
 
     # -------------------------------------------------------------------------------------- loops
@@ -460,9 +471,7 @@ class GaussianDiffusion:
     def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                      model_kwargs=None, device=None, progress=False, eta=0.0, langevin_fn=None,
                                      mask=None, x_start=None, gap=1, t_enc=None):
-        """diffusion.py:848-901."""
-        if langevin_fn:
-            raise NotImplementedError("langevin_fn is not used by the sampling path")
+        """diffusion.py:848-901 (`langevin_fn` is accepted and, as in the reference, never handed to ddim_sample :866-877)."""
         indices = list(range(self.num_timesteps))[::-1][::gap][slice(t_enc)]
         for sample, pred, _, _ in self._loop(_lib.STEP_DDIM, model, shape, noise, clip_denoised, denoised_fn,
                                              model_kwargs, device, progress, None, 0, True, mask, x_start, eta, indices,

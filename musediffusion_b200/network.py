@@ -225,13 +225,19 @@ class TransformerNetModel(nn.Module):
     def get_logits(self, hidden_repr):
         """network.py:91-93 (logits_mode 1): lm_head(x) = x E^T + b as ONE tcgen05 GEMM over split-bf16 operands
         (all four partial products of x = xh + xl, E = Eh + El with fp32 accumulation: fp32-grade logits)."""
-        if self.logits_mode != 1:
-            raise NotImplementedError("logits_mode 2 is not used by the sampling path (run/sample.py:219)")
+        if self.logits_mode not in (1, 2):
+            raise NotImplementedError                                  # network.py:105-106
         pk = self.weight_pack()
         V, D = pk.E.shape
         A = ops.split_bf16(hidden_repr.reshape(-1, D), copies=2)     # [M, 4D] = [xh|xl|xh|xl]
-        out = ops.linear(A, pk.E_split, pk.lm_bias_pad, _lib.EPI_BIAS, out_dtype=torch.float32)
-        return out[:, :V].reshape(*hidden_repr.shape[:-1], V).to(hidden_repr.dtype)
+        if self.logits_mode == 1:
+            out = ops.linear(A, pk.E_split, pk.lm_bias_pad, _lib.EPI_BIAS, out_dtype=torch.float32)
+            return out[:, :V].reshape(*hidden_repr.shape[:-1], V).to(hidden_repr.dtype)
+        # logits_mode 2 (network.py:94-104): minus the Euclidean distance to every embedding row, [B, L, V]
+        dot = ops.linear(A, pk.E_split, None, _lib.EPI_BIAS, out_dtype=torch.float32)
+        esq = ops.split_embedding(pk.E).sqnorm
+        out = ops.dist_scores(hidden_repr.reshape(-1, D), dot, esq, V)
+        return out.reshape(*hidden_repr.shape[:-1], V).to(hidden_repr.dtype)
 
     def decode_tokens(self, hidden_repr, want_margin=False):
         """get_logits + argmax(-1) (run/sample.py:219-220) fused into one kernel; logits never reach HBM."""
@@ -263,6 +269,18 @@ class TransformerNetModel(nn.Module):
         return self.denoise(x, timesteps).type(x.dtype)
 
     # ------------------------------------------------------------------------------------------ engine
+    # sequences are independent, so a large batch runs through the encoder in passes of at most `max_tokens_per_pass` tokens
+    # that share ONE activation workspace (FFN-mid alone is 35 GB at 1024 sequences of the scaled
+    # config).  The default is the bench operating point (256 x 2096 tokens): a 512-sequence batch in one pass measured
+    # 5.8 % slower per sequence than two passes of 256 (round 1 step sweep).
+    max_tokens_per_pass = 256 * 2096
+
+    def pass_size(self, B, L):
+        """sequences per encoder pass: equal-sized passes, each within the token cap (at least one sequence)."""
+        cap = max(1, int(self.max_tokens_per_pass) // L) if self.max_tokens_per_pass else B
+        n_pass = -(-B // cap)
+        return -(-B // n_pass)
+
     def denoise(self, x, timesteps, x_bf16=None, uniform_t=False, out=None):
         """The CUDA forward.  `x_bf16`: optional bf16 copy of x already produced by the posterior-step kernel;
         `uniform_t`: all rows share timesteps[0] (true inside the sampling loops) -> one time-embedding row."""
@@ -272,32 +290,42 @@ class TransformerNetModel(nn.Module):
         B, L, D = x.shape
         if L > self.config.max_position_embeddings:
             raise ValueError("sequence length %d exceeds seq_len %d" % (L, self.config.max_position_embeddings))
-        M, H = B * L, pk.H
-        ws = self.workspace(M)
-        E = _lib
-        xb = x_bf16.view(M, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(M, D).float())
         t = timesteps.reshape(-1).float()
         if not uniform_t:
             if t.numel() == 1:
                 uniform_t = True                  # one timestep for the whole batch (GaussianDiffusion._step allows it)
             elif t.numel() != B:                  # the reference asserts t.shape == (B,) (network.py:137 via timestep_embedding)
                 raise ValueError("timesteps has %d entries for a batch of %d sequences" % (t.numel(), B))
+        if out is None:
+            out = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
+        out = out.view(B, L, D)
+        xb = x_bf16.view(B, L, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(B * L, D).float()).view(B, L, D)
         temb = ops.timestep_mlp(t[:1] if uniform_t else t, pk.t0_w, pk.t0_b, pk.t2_w, pk.t2_b)
-        ops.linear(xb, pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=ws.a)
-        ops.linear(ws.a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,
-                   temb_stride=0 if uniform_t else H, L=L, out=ws.b)
-        h, h1, pre = ws.a, ws.c, ws.b
+        mb = self.pass_size(B, L)
+        ws = self.workspace(mb * L)
+        for s in range(0, B, mb):
+            e = min(B, s + mb)
+            self._encoder_pass(pk, ws, xb[s:e], temb if uniform_t else temb[s:e], uniform_t, out[s:e])
+        return out
+
+    def _encoder_pass(self, pk, ws, xb, temb, uniform_t, out):
+        """network.py:141-157 for a contiguous slice of sequences: xb bf16 [b, L, D] -> out fp32 [b, L, D]."""
+        b, L, D = xb.shape
+        M, H = b * L, pk.H
+        E = _lib
+        a, bb, c, qkv, mid = ws.a[:M], ws.b[:M], ws.c[:M], ws.qkv[:M], ws.mid[:M]
+        ops.linear(xb.view(M, D), pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=a)
+        ops.linear(a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,
+                   temb_stride=0 if uniform_t else H, L=L, out=bb)
+        h, h1, pre = a, c, bb
         ops.layernorm(pre, pk.ln_g, pk.ln_b, pk.eps, out=h)
         for ly in pk.layers:
-            ops.linear(h, ly.wqkv, ly.bqkv, E.EPI_BIAS, out=ws.qkv)
-            ops.attention(ws.qkv, B, L, pk.NH, out=h1)                       # ctx -> h1 buffer
+            ops.linear(h, ly.wqkv, ly.bqkv, E.EPI_BIAS, out=qkv)
+            ops.attention(qkv, b, L, pk.NH, out=h1)                          # ctx -> h1 buffer
             ops.linear(h1, ly.wo, ly.bo, E.EPI_BIAS, out=pre)
             ops.layernorm(pre, ly.g1, ly.b1, pk.eps, resid=h, out=h1)        # LN(dense(ctx) + h)
-            ops.linear(h1, ly.w1, ly.bi, E.EPI_BIAS_GELU, out=ws.mid)
-            ops.linear(ws.mid, ly.w2, ly.b2, E.EPI_BIAS, out=pre)
+            ops.linear(h1, ly.w1, ly.bi, E.EPI_BIAS_GELU, out=mid)
+            ops.linear(mid, ly.w2, ly.b2, E.EPI_BIAS, out=pre)
             ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, resid=h1, out=h)       # LN(dense(mid) + h1)
         ops.linear(h, pk.dn1_w, pk.dn1_b, E.EPI_BIAS_TANH, out=h1)
-        if out is None:
-            out = torch.empty((M, D), dtype=torch.float32, device=x.device)
         ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS, out=out.view(M, D))
-        return out.view(B, L, D)

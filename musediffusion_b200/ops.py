@@ -189,6 +189,16 @@ def split_bf16(x, copies=1):
     return out
 
 
+def dist_scores(x, dot, esq, V):
+    """md_dist_scores: -sqrt(clamp(|E_v|^2 + |x|^2 - 2 x.E_v, 0)) -> fp32 [M, V] (get_logits, logits_mode 2)."""
+    x = _c(x, torch.float32)
+    dot = _c(dot, torch.float32)
+    _cu(x, dot, esq)
+    out = torch.empty((dot.shape[0], V), dtype=torch.float32, device=x.device)
+    K.dist_scores(x.reshape(dot.shape[0], -1), dot, esq, out)
+    return out
+
+
 class SplitEmbedding:
     """bf16 [Vp, 2D] = [Eh | El] split of an embedding matrix + |E_v|^2, built once per matrix version
     (md_embed_split); `logit_cst(bias)` gives the padded per-column constants of the argmax-logits mode."""

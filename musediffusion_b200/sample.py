@@ -160,37 +160,45 @@ def main(argv=None):
                            os.path.basename(args.model_path) + "." + args.mode + ".samples")
     os.makedirs(out_dir, exist_ok=True)
     tic = time.time()
-    tokens = []
     n_batches = (len(ids_all) + args.batch_size - 1) // args.batch_size
-    for bi in range(n_batches):
-        if bi % world != rank:                                    # run/sample.py:169-172
-            continue
-        sl = slice(bi * args.batch_size, (bi + 1) * args.batch_size)
-        diffusion.seq_offset = sl.start
-        cond = {"input_ids": torch.from_numpy(ids_all[sl]), "input_mask": torch.from_numpy(mask_all[sl])}
-        tok = sample_batch(model, diffusion, model_emb, cond, args.mode, args.step, targs.diffusion_steps,
-                           strength=getattr(args, "strength", 0.75), top_p=args.top_p, clamp_step=args.clamp_step,
-                           clip_denoised=args.clip_denoised, device=dev)
-        # token-level half of decode_batch (utils/decode_util.py:233-384), one launch for the whole batch, on the rank
-        # that sampled it: the reference does this row by row, rank after rank (run/sample.py:222-294)
-        prep = decode_util.prepare_batch(tok, cond["input_mask"].to(dev), strict_validation=args.strict_validation)
-        tokens.append((bi, tok.cpu().numpy(), prep.status, [n for n in prep.note_seqs], [m for m in prep.metas]))
-    gathered = dist.gather_objects(tokens)
+    L = ids_all.shape[1]
+    rows = []                                                     # rank 0: (batch index, tokens, mask) in batch order
+    for base in range(0, n_batches, world):                       # one round = `world` consecutive batches, one per rank
+        bi = base + rank                                          # run/sample.py:169-172: batch bi belongs to rank bi % world
+        tok_pad = torch.zeros((args.batch_size, L), dtype=torch.int32, device=dev)
+        if bi < n_batches:
+            sl = slice(bi * args.batch_size, (bi + 1) * args.batch_size)
+            diffusion.seq_offset = sl.start
+            cond = {"input_ids": torch.from_numpy(ids_all[sl]), "input_mask": torch.from_numpy(mask_all[sl])}
+            tok = sample_batch(model, diffusion, model_emb, cond, args.mode, args.step, targs.diffusion_steps,
+                               strength=getattr(args, "strength", 0.75), top_p=args.top_p, clamp_step=args.clamp_step,
+                               clip_denoised=args.clip_denoised, device=dev)
+            tok_pad[:tok.shape[0]] = tok.to(torch.int32)
+        # decoded ids of the round to every rank with ONE NCCL all-gather ([world, batch, L] int32), instead of the reference's
+        # rank-after-rank decode with a broadcast + barrier per rank (run/sample.py:222-294)
+        gathered = dist.all_gather_tokens(tok_pad).view(world, args.batch_size, L)
+        if rank == 0:
+            for k in range(min(world, n_batches - base)):
+                n = min(args.batch_size, len(ids_all) - (base + k) * args.batch_size)
+                rows.append((base + k, gathered[k, :n]))
     if rank == 0:
-        rows = sorted(sum(gathered, []), key=lambda p: p[0])
-        flat = [t for _, t, _, _, _ in rows]
-        np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
-        status = np.concatenate([st for _, _, st, _, _ in rows])
-        np.save(os.path.join(out_dir, "decode_status.npy"), status)
-        valid = 0
-        for bi, _, st, note_seqs, metas in rows:                  # same warnings / counts as batch_decode_* prints
-            for index in np.nonzero(st != decode_util.OK)[0]:
+        # token-level half of decode_batch (utils/decode_util.py:233-384): one launch per batch on the gathered ids
+        flat, statuses, valid = [], [], 0
+        for bi, tok in rows:
+            mask = torch.from_numpy(mask_all[bi * args.batch_size: bi * args.batch_size + tok.shape[0]]).to(dev)
+            prep = decode_util.prepare_batch(tok, mask, strict_validation=args.strict_validation)
+            st = prep.status
+            flat.append(tok.cpu().numpy().astype(np.int64))
+            statuses.append(st)
+            for index in np.nonzero(st != decode_util.OK)[0]:         # same warnings / counts as batch_decode_* prints
                 print("<Warning> Batch %d Index %d (Original: %d) - Generation Failure: %s"
                       % (bi, index, bi * args.batch_size + index, decode_util.STATUS_TEXT[int(st[index])]))
-            for index in np.nonzero(st == decode_util.OK)[0]:     # what decode_event_sequence (:201-205) would be handed
+            for index in np.nonzero(st == decode_util.OK)[0]:         # what decode_event_sequence (:201-205) would be handed
                 np.savez(os.path.join(out_dir, "%07d_batch%05d_%04d.notes.npz" % (bi * args.batch_size + index, bi, index)),
-                         note_seq=note_seqs[index], encoded_meta=metas[index])
+                         note_seq=prep.note_seqs[index], encoded_meta=prep.metas[index])
             valid += int((st == decode_util.OK).sum())
+        np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
+        np.save(os.path.join(out_dir, "decode_status.npy"), np.concatenate(statuses))
         print("### Total takes %.2fs; %d sequences (%d valid) -> %s"
               % (time.time() - tic, sum(len(t) for t in flat), valid, out_dir))
     dist.barrier()

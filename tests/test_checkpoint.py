@@ -89,3 +89,41 @@ def test_packed_weights_drive_the_same_forward(tmp_path, golden_dir):
     p2 = O.make_random_params(seed=5, seq_len=200)
     m2.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in p2.items()})
     assert not torch.equal(m2(x, t), y1)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
+def test_cli_samples_from_checkpoint_and_from_pack(tmp_path, golden_dir):
+    """`python -m musediffusion_b200 modification|generation` (flag names of config/sample.py:93-209) on a reference-style model
+    directory and on the pack written from it: same seed -> same decoded ids; encoder passes of any size give the same bits."""
+    d = tmp_path / "m"
+    d.mkdir()
+    raw = json.load(open(os.path.join(golden_dir, "training_args_default.json")))
+    raw["seq_len"] = 64
+    (d / "training_args.json").write_text(json.dumps(raw))
+    p = O.make_random_params(seed=12, seq_len=64)
+    torch.save({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in p.items()}, str(d / "model_000000.pt"))
+    pack = cli_main(["pack", "--model_path", str(d / "model_000000.pt")])
+    outs = []
+    for mp, sub in ((str(d / "model_000000.pt"), "a"), (pack, "b")):
+        cli_main(["modification", "--model_path", mp, "--step", "10", "--batch_size", "3", "--num_batches", "2", "--strength", "1.0",
+                  "--out_dir", str(tmp_path / sub)])
+        base = tmp_path / sub / "m" / (os.path.basename(mp) + ".modification.samples")
+        tok = np.load(str(base / "tokens.npy"))
+        st = np.load(str(base / "decode_status.npy"))
+        assert tok.shape == (6, 64) and tok.dtype == np.int64 and st.shape == (6,)
+        outs.append(tok)
+    assert np.array_equal(outs[0], outs[1])
+    cli_main(["generation", "--model_path", pack, "--step", "20", "--batch_size", "2", "--num_samples", "4", "--out_dir", str(tmp_path / "g")])
+    gtok = np.load(str(tmp_path / "g" / "m" / (os.path.basename(pack) + ".generation.samples") / "tokens.npy"))
+    assert gtok.shape == (4, 64)
+    # micro-batched encoder passes == one pass, bit for bit
+    dev = torch.device("cuda:0")
+    m, _, _ = load_model(pack, dev)
+    x = torch.randn(5, 64, 128, device=dev)
+    t = torch.tensor([10.0, 500.0, 3.0, 999.0, 77.0], device=dev)
+    one = m.denoise(x, t).clone()
+    m.max_tokens_per_pass = 2 * 64
+    assert m.pass_size(5, 64) == 2
+    assert torch.equal(m.denoise(x, t), one)
+    assert torch.equal(m.denoise(x, t[:1].expand(5).contiguous(), uniform_t=True), m.denoise(x, t[:1].expand(5).contiguous()))

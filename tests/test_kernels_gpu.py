@@ -354,13 +354,13 @@ def test_philox_noise_distribution(top_p):
 
 
 def test_untruncated_normal_tails_are_symmetric_and_bounded():
-    """2^28 untruncated draws hit every extreme 24-bit pattern (2^24 - 1 and 0) with probability 1 - e^-16: the quantile is
-    evaluated from the tail probability 0.5 - |q|, so both tails stop at |n| = Phi^-1(2^-25) = 5.42 (a quantile taken from
-    p = q + 0.5 rounds the topmost draw to p = 1 and yields a +11.5 sigma outlier)."""
+    """2^28 untruncated draws hit both extreme 23-bit patterns with probability 1 - e^-32: the quantile is evaluated from the
+    tail probability 0.5 - |q|, so both tails stop at |n| = Phi^-1(2^-24) = 5.30 (a quantile taken from p = q + 0.5 rounds the
+    topmost draw to p = 1 and yields a +11.5 sigma outlier)."""
     n = 1 << 28
     a = ops.fill_normal((n,), DEV, seed=7, step_counter=1, top_p=0.0)
     hi, lo = float(a.max()), float(a.min())
-    assert 5.0 < hi < 5.5 and -5.5 < lo < -5.0, (lo, hi)
+    assert 5.2 < hi < 5.4 and -5.4 < lo < -5.2, (lo, hi)
     assert abs(hi + lo) < 0.05, (lo, hi)
     for thr in (3.0, 4.0):                                       # tail masses agree with the normal law on both sides
         up, dn = int((a > thr).sum()), int((a < -thr).sum())

@@ -26,6 +26,7 @@ targs = SimpleNamespace(hidden_dim=128, hidden_t_dim=128, vocab_size=729, seq_le
                         predict_xstart=True)
 torch.manual_seed(0)
 model, diffusion = create_model_and_diffusion(targs)
+diffusion.use_cuda_graph = False          # plain launches: ncu's -k / -s / -c then count kernels in program order
 model.eval().requires_grad_(False).to(dev)
 emb = build_model_emb(model, dev)
 c = make_synthetic_batch("modification", a.batch, a.seq_len, seed=105)

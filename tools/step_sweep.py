@@ -1,5 +1,5 @@
 """BASELINE.json config 4: sampling-step sweep through the public API (sample_batch) to separate per-step kernel cost
-from fixed overhead: time = a + b * steps.   python tools/step_sweep.py --batch 512 --steps 25 50 100 200"""
+from fixed overhead: time = a + b * steps.   python tools/step_sweep.py --batch 512 --steps 50 200 1000 2000   (2000 = the full DDPM chain)"""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,7 +12,7 @@ from musediffusion_b200.synthetic import make_synthetic_batch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=512)
-ap.add_argument("--steps", type=int, nargs="+", default=[25, 50, 100, 200])
+ap.add_argument("--steps", type=int, nargs="+", default=[50, 200, 1000, 2000])
 ap.add_argument("--mode", default="modification")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -34,7 +34,7 @@ for st in a.steps:
     tok = sample_batch(model, diffusion, emb, cond, a.mode, st, T, strength=1.0).cpu()
     torch.cuda.synchronize()
     rows.append((st, time.perf_counter() - tic))
-    print("steps %5d (DDIM gap %3d): %.3f s  -> %.3f sequences/s" % (st, T // st, rows[-1][1], a.batch / rows[-1][1]))
+    print("steps %5d (%s): %.3f s  -> %.4f sequences/s, %.2f ms/step" % (st, "DDPM" if st == T else "DDIM gap %d" % (T // st), rows[-1][1], a.batch / rows[-1][1], 1e3 * rows[-1][1] / st), flush=True)
 x = np.array([r[0] for r in rows], dtype=np.float64); y = np.array([r[1] for r in rows])
 b, c = np.polyfit(x, y, 1)
 print(json.dumps({"config": "step sweep, batch %d, %s, DDIM" % (a.batch, a.mode), "fit": "time = a + b*steps",
