@@ -9,8 +9,8 @@ cap() {  # name regex skip count
     python tools/profile_step.py --batch $B --steps 3 > gpurun_out/ncu_$1.log 2>&1; echo "ncu $1 rc=$?"
 }
 cap attention attention_kernel 14 1          # layer 2 of step 1
-cap ffn1 'gemm_pair_kernel<1' 14 1             # FFN1 (bias + erf-GELU epilogue)
-cap gemm_epi0 'gemm_pair_kernel<0' 39 3     # step 1, layer 1: QKV (K=768,N=2304), out-proj (768x768), FFN2 (K=3072)
+cap ffn1 'gemm_pair_kernel<.int.1' 14 1          # FFN1 (bias + erf-GELU epilogue)
+cap gemm_epi0 'gemm_pair_kernel<.int.0' 39 3     # step 1, layer 1: QKV (K=768,N=2304), out-proj (768x768), FFN2 (K=3072)
 cap round_tc round_tc_kernel 1 1
 cap posterior posterior_step 1 1
 cap layernorm layernorm_kernel 30 1
