@@ -328,7 +328,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "sequences/sec full reverse-diffusion sampling", "value": value, "unit": "sequences/s",
                 "n_gpus": world, "steps": timed_steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(B, world, mode=args.mode), "ms_per_denoiser_step": ms_step, "ms_decode": ms_decode,
                 "step_tflops": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
                 "clocks": sampler.summary(), "gpu_launches": launches,
@@ -415,6 +415,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="sequences per step for --impl reference (BASELINE.md section 3: 4)")
     ap.add_argument("--mode", default="modification", choices=["modification", "generation"],
                     help="modification = BASELINE.json configs[1] (default); generation = configs[2] (sample_generation path)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="label of the run: weak = --batch sequences per GPU whatever N (default); strong = the caller divides a "
+                         "fixed total by N itself (BASELINE.json configs[4]: 2048 sequences over 2/4/8 GPUs)")
     ap.add_argument("--full-chain", action="store_true", help="run all 2000 chain steps instead of extrapolating")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
