@@ -31,6 +31,8 @@ typedef struct CUstream_st* cudaStream_t;
 #define MD_EPI_BIAS_TANH 2     /* tanh(y)                input_up_proj / output_down_proj, network.py:69-70,83-84 */
 /* (3 is reserved: the residual add of HF BertSelfOutput / BertOutput is fused into md_layernorm_bf16 instead) */
 #define MD_EPI_BIAS_POS_TIME 4 /* y + pos[l] + temb[b]   network.py:146-148 pre-LayerNorm sum            */
+#define MD_EPI_BIAS_SPLIT 5    /* out = bf16 [M, 2N] = [hi | lo] of y (hi = bf16(y), lo = bf16(y - hi)): the last Linear of
+                                * output_down_proj (network.py:85) feeding md_round_argmin_tc without an fp32 round trip */
 
 /* modes of md_posterior_step */
 #define MD_STEP_DDPM 0 /* GaussianDiffusion.p_sample,    models/diffusion.py:349-404 */
@@ -100,7 +102,8 @@ int md_dist_scores(const float* x, const float* dot, const float* esq, float* ou
  *   md_round_argmin_tc: mode 0: idx[m] = argmin_v (cst[v] - 2 x_m.E_v), cst = sqnorm  (rounding.py:21-28; |x_m|^2 is
  *     constant per row, the reference's clamp(dist, 0) only creates ties on bit-exact hits);
  *     mode 1: idx[m] = argmax_v (x_m.E_v + cst[v]), cst = lm_head bias padded with -inf  (network.py:91-93 + argmax).
- *     x2_ws: bf16 [M, 2D] scratch.  Lowest index wins ties.  D must be a multiple of 64. */
+ *     x2_ws: bf16 [M, 2D] scratch; with x == NULL it must already hold the [hi | lo] split of x (MD_EPI_BIAS_SPLIT) and
+ *     the split pass is skipped.  Lowest index wins ties.  D must be a multiple of 64. */
 /* fp32 [rows, D] -> bf16 [rows, copies * 2D]: `copies` repetitions of the two-term split [hi | lo], hi = bf16(x),
  * lo = bf16(x - hi)  (operand of the split-bf16 contractions: rounding, decode, get_logits). */
 int md_split_bf16(const float* x, void* out_bf16, int64_t rows, int D, int copies, cudaStream_t stream);

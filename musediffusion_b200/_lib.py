@@ -42,7 +42,7 @@ SIGNATURES = {
     "md_onnc": [c_p, c_i, c_p, c_p, c_p],
 }
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_POS_TIME = 0, 1, 2, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_TANH, EPI_BIAS_POS_TIME, EPI_BIAS_SPLIT = 0, 1, 2, 4, 5
 STEP_DDPM, STEP_DDIM = 0, 1
 MAX_CONST_T = 2048
 

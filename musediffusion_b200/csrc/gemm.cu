@@ -239,6 +239,39 @@ MD_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                     for (int j = 0; j < kChunkCols; ++j) v[j] = epi_act<EPI>(v[j]);
                 }
                 if (p.debug_skip == 2) continue;
+                if (EPI == MD_EPI_BIAS_SPLIT) {
+                    // out = bf16 [M, 2N] = [hi | lo], hi = bf16(v), lo = bf16(v - hi): the split-bf16 operand of the rounding
+                    // contraction, emitted here so that the fp32 model output never makes an HBM round trip.  Two half-slab
+                    // stores per chunk (columns n and N + n), the same double buffering as the plain bf16 path.
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint8_t* dstp = slab + buf * 2048;
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                        const uint32_t row_addr = smem_u32(dstp) + lane * 64;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float a0 = v[k * 8 + 2 * e], a1 = v[k * 8 + 2 * e + 1];
+                                const uint32_t hi = pack_bf16x2(a0, a1);
+                                if (part == 0) w[e] = hi;
+                                else { const float2 hf = unpack_bf16x2(hi); w[e] = pack_bf16x2(a0 - hf.x, a1 - hf.y); }
+                            }
+                            const uint32_t addr = row_addr + ((k ^ ((lane >> 1) & 3)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && p.debug_skip == 0) {
+                            tma_store_2d(&tmC, dstp, n + part * p.N, row0);
+                            tma_store_commit();
+                        }
+                        buf ^= 1;
+                    }
+                    continue;
+                }
                 // the TMA store that last used this staging buffer must have finished READING shared memory
                 uint8_t* dst = OUT_F32 ? slab : slab + buf * 2048;
                 if (lane == 0) { if (OUT_F32) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
@@ -478,6 +511,7 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
         case MD_EPI_BIAS_GELU: return launch_gemm<BN, MD_EPI_BIAS_GELU, OUT_F32>(tmA, tmB, tmC, a, s);
         case MD_EPI_BIAS_TANH: return launch_gemm<BN, MD_EPI_BIAS_TANH, OUT_F32>(tmA, tmB, tmC, a, s);
         case MD_EPI_BIAS_POS_TIME: return launch_gemm<BN, MD_EPI_BIAS_POS_TIME, OUT_F32>(tmA, tmB, tmC, a, s);
+        case MD_EPI_BIAS_SPLIT: return launch_gemm<BN, MD_EPI_BIAS_SPLIT, false>(tmA, tmB, tmC, a, s);
     }
     set_last_error("md_linear_bf16: unknown epilogue %d", epi);
     return MD_ERR_ARG;
@@ -499,11 +533,13 @@ extern "C" __attribute__((visibility("default"))) int md_linear_bf16(const void*
     const int BN = (N % 256 == 0 || N > 512) ? 256 : 128;
     // CTA pairs (cta_group::2) for the large regular shapes; MD_GEMM_PAIR=0 forces the single-CTA kernel
     static const int use_pair = env_int("MD_GEMM_PAIR", 1);
-    const bool pair = use_pair && N % 256 == 0 && M >= 1024 && !out_is_f32;
+    const bool split = (epilogue == MD_EPI_BIAS_SPLIT);
+    if (split && out_is_f32) { set_last_error("md_linear_bf16: the split epilogue writes bf16 [M, 2N]"); return MD_ERR_ARG; }
+    const bool pair = use_pair && N % 256 == 0 && M >= 1024 && !out_is_f32 && !split;
     CUtensorMap tmA, tmB, tmC;
     if (int e = make_tmap_2d(&tmA, A, 0, M, K, K, BM, BK)) return e;
     if (int e = make_tmap_2d(&tmB, W, 0, N, K, K, pair ? 128 : BN, BK)) return e;
-    if (int e = make_tmap_2d(&tmC, out, out_is_f32, M, N, N, 32, 32)) return e;
+    if (int e = make_tmap_2d(&tmC, out, out_is_f32, M, split ? 2 * N : N, split ? 2 * N : N, 32, 32)) return e;
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.L = L > 0 ? L : 1;
     a.bias = bias; a.pos = pos; a.temb = temb; a.temb_stride = temb_stride; a.out = out;

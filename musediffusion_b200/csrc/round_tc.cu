@@ -264,8 +264,10 @@ extern "C" __attribute__((visibility("default"))) int md_round_argmin_tc(const f
     if (mode != 0 && mode != 1) { set_last_error("md_round_argmin_tc: mode must be 0 (argmin distance) or 1 (argmax logit)"); return MD_ERR_ARG; }
     if (M == 0) return MD_OK;
     const int Vp = md_round_tc_padded_vocab(V);
-    split_bf16_kernel<<<ew_grid2(M * (D / 4)), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(x2_ws), M, D, 1);
-    if (int e = check_cuda(cudaGetLastError(), "split_bf16 launch")) return e;
+    if (x != nullptr) {       // x == NULL: x2_ws already holds the split (written by the producing GEMM's epilogue)
+        split_bf16_kernel<<<ew_grid2(M * (D / 4)), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(x2_ws), M, D, 1);
+        if (int e = check_cuda(cudaGetLastError(), "split_bf16 launch")) return e;
+    }
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d(&tmA, x2_ws, 0, (uint64_t)M, 2 * D, 2 * D, RT_BM, RT_BK)) return e;
     if (int e = make_tmap_2d(&tmB, E2, 0, (uint64_t)Vp, 2 * D, 2 * D, RT_BN, RT_BK)) return e;

@@ -76,7 +76,7 @@ def _layernorm_bf16(x, resid, gamma, beta, eps, out):
 # ------------------------------------------------------------------------------------------------ contractions
 def _linear_bf16(A, W, bias, out, epilogue, pos, temb, temb_stride, L):
     M, K = A.shape
-    N = W.shape[0]
+    N = W.shape[0]                                     # (the split epilogue writes out = bf16 [M, 2N])
     launch("md_linear_bf16", _p(A), _p(W), _p(bias), _p(out), M, N, K, epilogue, int(out.dtype == torch.float32), _p(pos), _p(temb),
            temb_stride, L, _stream(), detail="%dx%dx%d epi=%d" % (M, N, K, epilogue))
 
@@ -175,7 +175,7 @@ _define("logits_argmax(Tensor x, Tensor E, Tensor bias, Tensor(a!) tok, Tensor(b
 _define("split_bf16(Tensor x, Tensor(a!) out, int copies) -> ()", _split_bf16)
 _define("embed_split(Tensor E, Tensor(a!) E2, Tensor(b!) sqnorm) -> ()", _embed_split)
 _define("dist_scores(Tensor x, Tensor dot, Tensor esq, Tensor(a!) out) -> ()", _dist_scores)
-_define("round_argmin_tc(Tensor x, Tensor E2, Tensor cst, Tensor(a!) ws, Tensor(b!) idx, Tensor(c!)? margin, int V, int mode) -> ()",
+_define("round_argmin_tc(Tensor? x, Tensor E2, Tensor cst, Tensor(a!) ws, Tensor(b!) idx, Tensor(c!)? margin, int V, int mode) -> ()",
         _round_argmin_tc)
 _define("posterior_step(Tensor x_t, Tensor? idx, Tensor? pred, Tensor? E, Tensor? noise, int seed, int step_counter, int seq_offset, "
         "Tensor t, int t_stride, Tensor? mask, int mask_tok_stride, int mask_d_stride, Tensor? x_start, Tensor(a!) out, "

@@ -281,9 +281,11 @@ class TransformerNetModel(nn.Module):
         n_pass = -(-B // cap)
         return -(-B // n_pass)
 
-    def denoise(self, x, timesteps, x_bf16=None, uniform_t=False, out=None):
+    def denoise(self, x, timesteps, x_bf16=None, uniform_t=False, out=None, split_out=None):
         """The CUDA forward.  `x_bf16`: optional bf16 copy of x already produced by the posterior-step kernel;
-        `uniform_t`: all rows share timesteps[0] (true inside the sampling loops) -> one time-embedding row."""
+        `uniform_t`: all rows share timesteps[0] (true inside the sampling loops) -> one time-embedding row;
+        `split_out`: bf16 [B, L, 2D] — the last Linear then writes the [hi | lo] split of the output (operand of the
+        tensor-core rounding) INSTEAD of the fp32 tensor, and `split_out` is returned."""
         pk = self.weight_pack()
         if not x.is_cuda:
             raise _lib.MuseDiffLibraryError("TransformerNetModel.forward needs CUDA tensors (no CPU path)")
@@ -296,20 +298,24 @@ class TransformerNetModel(nn.Module):
                 uniform_t = True                  # one timestep for the whole batch (GaussianDiffusion._step allows it)
             elif t.numel() != B:                  # the reference asserts t.shape == (B,) (network.py:137 via timestep_embedding)
                 raise ValueError("timesteps has %d entries for a batch of %d sequences" % (t.numel(), B))
-        if out is None:
-            out = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
-        out = out.view(B, L, D)
+        if split_out is not None:
+            out = split_out.view(B, L, 2 * D)
+        else:
+            if out is None:
+                out = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
+            out = out.view(B, L, D)
         xb = x_bf16.view(B, L, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(B * L, D).float()).view(B, L, D)
         temb = ops.timestep_mlp(t[:1] if uniform_t else t, pk.t0_w, pk.t0_b, pk.t2_w, pk.t2_b)
         mb = self.pass_size(B, L)
         ws = self.workspace(mb * L)
         for s in range(0, B, mb):
             e = min(B, s + mb)
-            self._encoder_pass(pk, ws, xb[s:e], temb if uniform_t else temb[s:e], uniform_t, out[s:e])
+            self._encoder_pass(pk, ws, xb[s:e], temb if uniform_t else temb[s:e], uniform_t, out[s:e], split_out is not None)
         return out
 
-    def _encoder_pass(self, pk, ws, xb, temb, uniform_t, out):
-        """network.py:141-157 for a contiguous slice of sequences: xb bf16 [b, L, D] -> out fp32 [b, L, D]."""
+    def _encoder_pass(self, pk, ws, xb, temb, uniform_t, out, split=False):
+        """network.py:141-157 for a contiguous slice of sequences: xb bf16 [b, L, D] -> out fp32 [b, L, D]
+        (split: bf16 [b, L, 2D] = [hi | lo])."""
         b, L, D = xb.shape
         M, H = b * L, pk.H
         E = _lib
@@ -328,4 +334,7 @@ class TransformerNetModel(nn.Module):
             ops.linear(mid, ly.w2, ly.b2, E.EPI_BIAS, out=pre)
             ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, resid=h1, out=h)       # LN(dense(mid) + h1)
         ops.linear(h, pk.dn1_w, pk.dn1_b, E.EPI_BIAS_TANH, out=h1)
-        ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS, out=out.view(M, D))
+        if split:
+            ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS_SPLIT, out=out.view(M, 2 * D))
+        else:
+            ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS, out=out.view(M, D))

@@ -134,7 +134,9 @@ def linear(A, W, bias, epilogue=_lib.EPI_BIAS, out_dtype=BF16, pos=None, temb=No
     N = W.shape[0]
     assert W.shape[1] == Kd
     if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        out = torch.empty((M, 2 * N if epilogue == _lib.EPI_BIAS_SPLIT else N), dtype=out_dtype, device=A.device)
+    if epilogue == _lib.EPI_BIAS_SPLIT and (out.dtype != BF16 or out.shape[-1] != 2 * N):
+        raise _lib.MuseDiffLibraryError("md_linear_bf16: the split epilogue writes bf16 [M, 2N]")
     _cu(A, W, bias, out, pos, temb)
     K.linear_bf16(A, W, bias, out, epilogue, pos, temb, temb_stride, L)
     return out
@@ -243,14 +245,21 @@ def split_embedding(E):
     return hit[0]
 
 
-def round_argmin_tc(x, se, cst=None, mode=0, want_margin=False, out=None):
-    """tensor-core nearest-embedding ids (mode 0, cst = |E|^2) or argmax-logit ids (mode 1, cst = padded bias)."""
-    x = _c(x, torch.float32)
-    M = x.numel() // se.D
-    idx = out if out is not None else torch.empty((M,), dtype=torch.int32, device=x.device)
-    margin = torch.empty((M,), dtype=torch.float32, device=x.device) if want_margin else None
-    _cu(x)
-    K.round_argmin_tc(x, se.E2, se.sqnorm if cst is None else cst, se.workspace(M), idx, margin, se.V, mode)
+def round_argmin_tc(x, se, cst=None, mode=0, want_margin=False, out=None, presplit=None):
+    """tensor-core nearest-embedding ids (mode 0, cst = |E|^2) or argmax-logit ids (mode 1, cst = padded bias).
+    `presplit`: bf16 [M, 2D] = [hi | lo] of x already written by the producing GEMM (EPI_BIAS_SPLIT); x is then ignored."""
+    if presplit is not None:
+        assert presplit.dtype == BF16 and presplit.is_contiguous() and presplit.shape[-1] == 2 * se.D
+        M = presplit.numel() // (2 * se.D)
+        x, ws, dev = None, presplit.view(M, 2 * se.D), presplit.device
+    else:
+        x = _c(x, torch.float32)
+        M = x.numel() // se.D
+        ws, dev = se.workspace(M), x.device
+    idx = out if out is not None else torch.empty((M,), dtype=torch.int32, device=dev)
+    margin = torch.empty((M,), dtype=torch.float32, device=dev) if want_margin else None
+    _cu(x, ws)
+    K.round_argmin_tc(x, se.E2, se.sqnorm if cst is None else cst, ws, idx, margin, se.V, mode)
     return (idx, margin) if want_margin else idx
 
 

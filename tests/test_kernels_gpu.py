@@ -366,3 +366,64 @@ def test_untruncated_normal_tails_are_symmetric_and_bounded():
         up, dn = int((a > thr).sum()), int((a < -thr).sum())
         want = n * 0.5 * math.erfc(thr / math.sqrt(2.0))
         assert abs(up - want) < 6 * math.sqrt(want) and abs(dn - want) < 6 * math.sqrt(want), (thr, up, dn, want)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices in one process")
+def test_one_process_two_devices():
+    """The library keeps its state (schedule tables, SM count, raised shared-memory attributes) per device: one process that
+    alternates between cuda:0 and cuda:1 gets the right tables and launchable tcgen05 kernels on both."""
+    from musediffusion_b200.diffusion import SpacedDiffusion, get_named_beta_schedule, space_timesteps
+    outs = []
+    for dev_i, (sched, T) in enumerate([("sqrt", 2000), ("linear", 500)]):
+        dev = torch.device("cuda", dev_i)
+        with torch.cuda.device(dev):
+            d = SpacedDiffusion(use_timesteps=space_timesteps(T, [T]), betas=get_named_beta_schedule(sched, T), rescale_timesteps=True,
+                                predict_xstart=True)
+            g = torch.Generator(device="cpu").manual_seed(dev_i)
+            x0 = torch.randn(2, 40, 128, generator=g).to(dev)
+            n = torch.randn(2, 40, 128, generator=g).to(dev)
+            t = torch.tensor([T - 1, 3], device=dev)
+            q = d.q_sample(x0, t, noise=n)
+            s = O.make_schedule(sched, T)
+            want = O.q_sample(s, x0.cpu().numpy(), t.cpu().numpy(), n.cpu().numpy())
+            np.testing.assert_allclose(q.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+            outs.append((d, x0, t, n, want, dev))
+    # second round in the opposite order, no re-upload: device 0's tables must not have been displaced by device 1's
+    for d, x0, t, n, want, dev in outs[::-1] + outs:
+        with torch.cuda.device(dev):
+            np.testing.assert_allclose(d.q_sample(x0, t, noise=n).cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+    for dev_i in (1, 0, 1):
+        dev = torch.device("cuda", dev_i)
+        with torch.cuda.device(dev):
+            A = (torch.randn(300, 768, device=dev) * 0.1).to(torch.bfloat16)
+            W = (torch.randn(768, 768, device=dev) * 0.1).to(torch.bfloat16)
+            y = ops.linear(A, W, None)
+            assert rel_err(y, A.float() @ W.float().T) < 1.2e-2
+            qkv = (torch.randn(2 * 200, 3 * 128, device=dev) * 0.5).to(torch.bfloat16)
+            o = ops.attention(qkv, 2, 200, 2)
+            q_, k_, v_ = [t_.float().view(2, 200, 2, 64).transpose(1, 2) for t_ in qkv.split(128, dim=1)]
+            ref = (torch.softmax(q_ @ k_.transpose(-1, -2), dim=-1) @ v_).transpose(1, 2).reshape(400, 128)
+            assert rel_err(o, ref) < 1.5e-2
+            x = torch.randn(500, 128, device=dev)
+            E = torch.randn(729, 128, device=dev)
+            assert torch.equal(ops.round_argmin_tc(x, ops.SplitEmbedding(E)), ops.round_argmin(x, E))
+
+
+@pytest.mark.parametrize("M", [5000, 128, 77])
+def test_linear_split_epilogue_equals_split_of_fp32_output(M):
+    """MD_EPI_BIAS_SPLIT (last Linear of output_down_proj, network.py:85): bf16 [M, 2N] = [hi | lo] written by the GEMM epilogue
+    is bit-identical to md_split_bf16 of the fp32 output, and rounds to the same ids without the split pass."""
+    g = torch.Generator(device="cpu").manual_seed(M)
+    A = (torch.randn(M, 768, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(128, 768, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+    b = torch.randn(128, generator=g).to(DEV)
+    y32 = ops.linear(A, W, b, _lib.EPI_BIAS, out_dtype=torch.float32)
+    want = ops.split_bf16(y32, copies=1)
+    got = ops.linear(A, W, b, _lib.EPI_BIAS_SPLIT)
+    assert got.shape == (M, 256) and got.dtype == torch.bfloat16
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    E = torch.randn(729, 128, generator=g).to(DEV)
+    se = ops.SplitEmbedding(E)
+    assert torch.equal(ops.round_argmin_tc(None, se, presplit=got), ops.round_argmin_tc(y32, se))
+    with pytest.raises(_lib.MuseDiffLibraryError):
+        ops.linear(A, W, b, _lib.EPI_BIAS_SPLIT, out=torch.empty(M, 128, dtype=torch.bfloat16, device=DEV))
