@@ -54,6 +54,13 @@ int md_set_schedule(const float* tables, int T, cudaStream_t stream);
 /* ---- elementwise / small kernels ---- */
 /* fp32 -> bf16 cast of the state x_t (A operand of the first Linear).  n elements. */
 int md_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);
+/* Models with hidden_dim == encoder hidden size have no input_up_proj / output_down_proj (models/network.py:67-72, 81-86):
+ * md_add_pos_time: out[m, :] = bf16((pos[m % L, :] + x[m, :]) + temb[(m / L) * temb_stride, :])  — the pre-LayerNorm sum of
+ *   network.py:146-148 taken from the fp32 state itself (emb_x = x, :143-144);  x fp32 [M, H], pos fp32 [L, H].
+ * md_cast_bf16_f32: the last hidden state as the fp32 model output (h.type(x.dtype), :155-157).  n elements. */
+int md_add_pos_time(const float* x, const float* pos, const float* temb, int temb_stride, int L, int H, void* out_bf16, int64_t M,
+                    cudaStream_t stream);
+int md_cast_bf16_f32(const void* in_bf16, float* out, int64_t n, cudaStream_t stream);
 /* TransformerNetModel.get_embeds (models/network.py:88-89): out[m, :] = E[ids[m], :].  ids int32 or int64. */
 int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out, int64_t M, int V, int D,
                     cudaStream_t stream);

@@ -18,6 +18,8 @@ c_f = ctypes.c_float
 SIGNATURES = {
     "md_set_schedule": [c_p, c_i, c_p],
     "md_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
+    "md_cast_bf16_f32": [c_p, c_p, c_i64, c_p],
+    "md_add_pos_time": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_p],
     "md_embed_gather": [c_p, c_p, c_i, c_p, c_i64, c_i, c_i, c_p],
     "md_timestep_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "md_layernorm_bf16": [c_p, c_p, c_p, c_p, c_f, c_p, c_i64, c_i, c_p],

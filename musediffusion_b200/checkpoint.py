@@ -74,12 +74,14 @@ def pack_tensors(sd, num_heads):
     out["lm_bias"] = f32(sd["lm_head.bias"])
     out["t0_w"], out["t0_b"] = f32(sd["time_embed.0.weight"]), f32(sd["time_embed.0.bias"])
     out["t2_w"], out["t2_b"] = f32(sd["time_embed.2.weight"]), f32(sd["time_embed.2.bias"])
-    out["up1_w"], out["up1_b"] = bf(sd["input_up_proj.0.weight"]), f32(sd["input_up_proj.0.bias"])
-    out["up2_w"], out["up2_b"] = bf(sd["input_up_proj.2.weight"]), f32(sd["input_up_proj.2.bias"])
+    if "input_up_proj.0.weight" in sd:               # absent when hidden_dim == encoder hidden size (network.py:67-72)
+        out["up1_w"], out["up1_b"] = bf(sd["input_up_proj.0.weight"]), f32(sd["input_up_proj.0.bias"])
+        out["up2_w"], out["up2_b"] = bf(sd["input_up_proj.2.weight"]), f32(sd["input_up_proj.2.bias"])
     out["pos"] = f32(sd["position_embeddings.weight"])
     out["ln_g"], out["ln_b"] = f32(sd["LayerNorm.weight"]), f32(sd["LayerNorm.bias"])
-    out["dn1_w"], out["dn1_b"] = bf(sd["output_down_proj.0.weight"]), f32(sd["output_down_proj.0.bias"])
-    out["dn2_w"], out["dn2_b"] = bf(sd["output_down_proj.2.weight"]), f32(sd["output_down_proj.2.bias"])
+    if "output_down_proj.0.weight" in sd:            # absent when hidden_dim == encoder hidden size (network.py:81-86)
+        out["dn1_w"], out["dn1_b"] = bf(sd["output_down_proj.0.weight"]), f32(sd["output_down_proj.0.bias"])
+        out["dn2_w"], out["dn2_b"] = bf(sd["output_down_proj.2.weight"]), f32(sd["output_down_proj.2.bias"])
     H = sd["LayerNorm.weight"].shape[0]
     scale = 1.0 / math.sqrt(H // num_heads)          # exact power of two for head dim 64: folding it into W_q is lossless
     i = 0

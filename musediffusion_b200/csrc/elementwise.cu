@@ -514,6 +514,35 @@ __global__ void __launch_bounds__(256) fill_normal_kernel(float* out, int64_t n,
 }
 
 // ----------------------------------------------------------------------------------------------
+// hidden_dim == hidden_size models (network.py:141-149 without input_up_proj, :153-157 without output_down_proj):
+// pre-LayerNorm sum pos[l] + x + emb_t[b] straight from the fp32 state, and the bf16 -> fp32 cast of the last hidden state
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_pos_time_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ temb,
+                                                           int temb_stride, int L, int H, __nv_bfloat16* __restrict__ out, int64_t M) {
+    const int vec = H >> 2;
+    const int64_t total = M * vec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vec;
+        const int c = (int)(i - m * vec) << 2;
+        const int64_t b = m / L;
+        const int l = (int)(m - b * L);
+        const float4 v = ld_stream_f4(x + m * H + c);
+        const float4 pp = *reinterpret_cast<const float4*>(pos + (int64_t)l * H + c);
+        const float4 tt = *reinterpret_cast<const float4*>(temb + b * temb_stride + c);
+        // same association as the reference: (pos + emb_x) + emb_t   (network.py:147)
+        *reinterpret_cast<uint2*>(out + m * H + c) = make_uint2(pack_bf16x2((pp.x + v.x) + tt.x, (pp.y + v.y) + tt.y),
+                                                                pack_bf16x2((pp.z + v.z) + tt.z, (pp.w + v.w) + tt.w));
+    }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 u = *reinterpret_cast<const uint2*>(in + i * 4);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        st_stream_f4(out + i * 4, make_float4(a.x, a.y, b.x, b.y));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // casts / gather
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n4) {
@@ -766,6 +795,24 @@ extern "C" __attribute__((visibility("default"))) int md_cast_f32_bf16(const flo
     if (n == 0) return MD_OK;
     cast_f32_bf16_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n / 4);
     return check_cuda(cudaGetLastError(), "cast launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_cast_bf16_f32(const void* in, float* out, int64_t n, cudaStream_t stream) {
+    if (n % 4 != 0) { set_last_error("md_cast_bf16_f32: n must be a multiple of 4"); return MD_ERR_ARG; }
+    if (n == 0) return MD_OK;
+    cast_bf16_f32_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, n / 4);
+    return check_cuda(cudaGetLastError(), "cast launch");
+}
+
+extern "C" __attribute__((visibility("default"))) int md_add_pos_time(const float* x, const float* pos, const float* temb, int temb_stride, int L, int H,
+                               void* out_bf16, int64_t M, cudaStream_t stream) {
+    if (H % 4 != 0 || L <= 0 || M % L != 0 || pos == nullptr || temb == nullptr) {
+        set_last_error("md_add_pos_time: H %% 4 == 0, L > 0 dividing M, pos and temb required (H=%d L=%d)", H, L);
+        return MD_ERR_ARG;
+    }
+    if (M == 0) return MD_OK;
+    add_pos_time_kernel<<<ew_grid(M * (H / 4), 256), 256, 0, stream>>>(x, pos, temb, temb_stride, L, H, reinterpret_cast<__nv_bfloat16*>(out_bf16), M);
+    return check_cuda(cudaGetLastError(), "add_pos_time launch");
 }
 
 extern "C" __attribute__((visibility("default"))) int md_embed_gather(const float* E, const void* ids, int ids_is_i64, float* out, int64_t M, int V, int D,

@@ -59,6 +59,15 @@ def _cast_f32_bf16(x, out):
     launch("md_cast_f32_bf16", _p(x), _p(out), x.numel(), _stream())
 
 
+def _cast_bf16_f32(x, out):
+    launch("md_cast_bf16_f32", _p(x), _p(out), x.numel(), _stream())
+
+
+def _add_pos_time(x, pos, temb, temb_stride, L, out):
+    H = x.shape[-1]
+    launch("md_add_pos_time", _p(x), _p(pos), _p(temb), temb_stride, L, H, _p(out), x.numel() // H, _stream())
+
+
 def _embed_gather(E, ids, out):
     launch("md_embed_gather", _p(E), _p(ids), int(ids.dtype == torch.int64), _p(out), ids.numel(), E.shape[0], E.shape[1], _stream())
 
@@ -164,6 +173,8 @@ def _onnc(vectors, msim, most_sim):
 
 
 _define("cast_f32_bf16(Tensor x, Tensor(a!) out) -> ()", _cast_f32_bf16)
+_define("cast_bf16_f32(Tensor x, Tensor(a!) out) -> ()", _cast_bf16_f32)
+_define("add_pos_time(Tensor x, Tensor pos, Tensor temb, int temb_stride, int L, Tensor(a!) out) -> ()", _add_pos_time)
 _define("embed_gather(Tensor E, Tensor ids, Tensor(a!) out) -> ()", _embed_gather)
 _define("timestep_mlp(Tensor t, Tensor W0, Tensor b0, Tensor W2, Tensor b2, Tensor(a!) out, Tensor(b!) hid) -> ()", _timestep_mlp)
 _define("layernorm_bf16(Tensor x, Tensor? resid, Tensor gamma, Tensor beta, float eps, Tensor(a!) out) -> ()", _layernorm_bf16)
@@ -195,7 +206,7 @@ _define("sequence_metrics(Tensor notes, Tensor note_len, Tensor meta, Tensor(a!)
         _sequence_metrics)
 _define("onnc(Tensor vectors, Tensor(a!)? msim, Tensor(b!) most_sim) -> ()", _onnc)
 
-OP_NAMES = ["cast_f32_bf16", "embed_gather", "timestep_mlp", "layernorm_bf16", "linear_bf16", "attention_bf16", "round_argmin",
+OP_NAMES = ["cast_f32_bf16", "cast_bf16_f32", "add_pos_time", "embed_gather", "timestep_mlp", "layernorm_bf16", "linear_bf16", "attention_bf16", "round_argmin",
             "logits_argmax", "split_bf16", "dist_scores", "embed_split", "round_argmin_tc", "posterior_step", "xstart_from_eps", "q_sample",
             "fill_normal", "step_advance", "decode_prepare", "merge_and_mask", "sequence_metrics", "onnc"]
 ops = getattr(torch.ops, NAMESPACE)

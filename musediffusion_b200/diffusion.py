@@ -384,8 +384,9 @@ class GaussianDiffusion:
         xb = ops.cast_bf16(x)
         # x0-predicting model: the last Linear emits the [hi | lo] bf16 split that the rounding contraction consumes, the fp32
         # model output never exists; an eps-predicting model needs it in fp32 for x0 = sr x_t - srm1 eps first
-        mo = torch.empty_like(x) if not self.predict_xstart else None
-        mo_split = torch.empty(x.shape[:-1] + (2 * x.shape[-1],), dtype=torch.bfloat16, device=dev) if self.predict_xstart else None
+        use_split = self.predict_xstart and fast.weight_pack().has_down
+        mo = torch.empty_like(x) if not use_split else None
+        mo_split = torch.empty(x.shape[:-1] + (2 * x.shape[-1],), dtype=torch.bfloat16, device=dev) if use_split else None
         cursor = torch.zeros(1, dtype=torch.int32, device=dev)
         t_cur = torch.zeros(1, dtype=torch.int32, device=dev)
         tm_cur = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -401,12 +402,14 @@ class GaussianDiffusion:
 
         def one_step():
             ops.step_advance(cursor, t_idx, t_model, t_cur, tm_cur, ctr_cur, ctr_base)
-            if self.predict_xstart:
+            if use_split:
                 fast.denoise(x, tm_cur, x_bf16=xb, uniform_t=True, split_out=mo_split)
                 ops.round_argmin_tc(None, se, out=idx, presplit=mo_split)
             else:
                 out = fast.denoise(x, tm_cur, x_bf16=xb, uniform_t=True, out=mo)
-                ops.round_argmin_tc(ops.xstart_from_eps(x, out, t_cur), se, out=idx)
+                if not self.predict_xstart:
+                    out = ops.xstart_from_eps(x, out, t_cur)
+                ops.round_argmin_tc(out, se, out=idx)
             ops.posterior_step(x, t_cur, mode, idx=idx, E=E, seed=seed, seq_offset=self.seq_offset, mask=mask, x_start=x_start,
                                eta=eta, clip=clip_denoised, top_p=tp, out=x, out_bf16=xb, step_counter_dev=ctr_cur)
 

@@ -82,9 +82,13 @@ class WeightPack:
         self.H = model.hidden_size
         self.NH = model.num_heads
         self.eps = model.layer_norm_eps
-        for name in ("E", "lm_bias", "t0_w", "t0_b", "t2_w", "t2_b", "up1_w", "up1_b", "up2_w", "up2_b", "pos", "ln_g", "ln_b",
-                     "dn1_w", "dn1_b", "dn2_w", "dn2_b"):
+        for name in ("E", "lm_bias", "t0_w", "t0_b", "t2_w", "t2_b", "pos", "ln_g", "ln_b"):
             setattr(self, name, tensors[name])
+        for name in ("up1_w", "up1_b", "up2_w", "up2_b", "dn1_w", "dn1_b", "dn2_w", "dn2_b"):
+            setattr(self, name, tensors.get(name))          # None: hidden_dim == hidden size, no up / down projection
+        self.has_up, self.has_down = self.up1_w is not None, self.dn1_w is not None
+        if self.has_up != (model.input_dims != model.hidden_size) or self.has_down != (model.output_dims != model.hidden_size):
+            raise ValueError("weight pack and model disagree about input_up_proj / output_down_proj")
         self.layers = []
         i = 0
         while "l%d.wqkv" % i in tensors:
@@ -144,8 +148,6 @@ class TransformerNetModel(nn.Module):
         self.layer_norm_eps = cfg.layer_norm_eps
         if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size // cfg.num_attention_heads != 64:
             raise NotImplementedError("the fused attention kernel is specialised for head dim 64")
-        if input_dims == cfg.hidden_size or output_dims == cfg.hidden_size:
-            raise NotImplementedError("hidden_dim == encoder hidden size (no up/down projection) is not built yet")
 
         self.word_embedding = nn.Embedding(vocab_size, input_dims)
         self.lm_head = nn.Linear(input_dims, vocab_size)
@@ -154,15 +156,17 @@ class TransformerNetModel(nn.Module):
         time_embed_dim = hidden_t_dim * 4
         self.time_embed = nn.Sequential(nn.Linear(hidden_t_dim, time_embed_dim), nn.SiLU(),
                                         nn.Linear(time_embed_dim, cfg.hidden_size))
-        self.input_up_proj = nn.Sequential(nn.Linear(input_dims, cfg.hidden_size), nn.Tanh(),
-                                           nn.Linear(cfg.hidden_size, cfg.hidden_size))
+        if input_dims != cfg.hidden_size:                                # network.py:67-72
+            self.input_up_proj = nn.Sequential(nn.Linear(input_dims, cfg.hidden_size), nn.Tanh(),
+                                               nn.Linear(cfg.hidden_size, cfg.hidden_size))
         self.input_transformers = _Encoder(cfg)
         self.dropout = nn.Dropout(dropout)
         self.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).expand((1, -1)))
         self.position_embeddings = nn.Embedding(cfg.max_position_embeddings, cfg.hidden_size)
         self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        self.output_down_proj = nn.Sequential(nn.Linear(cfg.hidden_size, cfg.hidden_size), nn.Tanh(),
-                                              nn.Linear(cfg.hidden_size, output_dims))
+        if output_dims != cfg.hidden_size:                               # network.py:81-86
+            self.output_down_proj = nn.Sequential(nn.Linear(cfg.hidden_size, cfg.hidden_size), nn.Tanh(),
+                                                  nn.Linear(cfg.hidden_size, output_dims))
         self._pack = None
         self._pack_key = None
         self._pack_refs = None
@@ -298,13 +302,18 @@ class TransformerNetModel(nn.Module):
                 uniform_t = True                  # one timestep for the whole batch (GaussianDiffusion._step allows it)
             elif t.numel() != B:                  # the reference asserts t.shape == (B,) (network.py:137 via timestep_embedding)
                 raise ValueError("timesteps has %d entries for a batch of %d sequences" % (t.numel(), B))
+        if split_out is not None and not pk.has_down:
+            raise ValueError("split_out needs the output_down_proj GEMM (hidden_dim != hidden size)")
         if split_out is not None:
             out = split_out.view(B, L, 2 * D)
         else:
             if out is None:
                 out = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
             out = out.view(B, L, D)
-        xb = x_bf16.view(B, L, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(B * L, D).float()).view(B, L, D)
+        if pk.has_up:
+            xb = x_bf16.view(B, L, D) if x_bf16 is not None else ops.cast_bf16(x.reshape(B * L, D).float()).view(B, L, D)
+        else:
+            xb = x.float().contiguous()                   # emb_x = x (network.py:143-144): the fp32 state feeds the pre-LN sum
         temb = ops.timestep_mlp(t[:1] if uniform_t else t, pk.t0_w, pk.t0_b, pk.t2_w, pk.t2_b)
         mb = self.pass_size(B, L)
         ws = self.workspace(mb * L)
@@ -320,9 +329,12 @@ class TransformerNetModel(nn.Module):
         M, H = b * L, pk.H
         E = _lib
         a, bb, c, qkv, mid = ws.a[:M], ws.b[:M], ws.c[:M], ws.qkv[:M], ws.mid[:M]
-        ops.linear(xb.view(M, D), pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=a)
-        ops.linear(a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,
-                   temb_stride=0 if uniform_t else H, L=L, out=bb)
+        if pk.has_up:
+            ops.linear(xb.view(M, D), pk.up1_w, pk.up1_b, E.EPI_BIAS_TANH, out=a)
+            ops.linear(a, pk.up2_w, pk.up2_b, E.EPI_BIAS_POS_TIME, pos=pk.pos, temb=temb,
+                       temb_stride=0 if uniform_t else H, L=L, out=bb)
+        else:
+            ops.add_pos_time(xb.view(M, D), pk.pos, temb, 0 if uniform_t else H, L, bb)
         h, h1, pre = a, c, bb
         ops.layernorm(pre, pk.ln_g, pk.ln_b, pk.eps, out=h)
         for ly in pk.layers:
@@ -333,6 +345,9 @@ class TransformerNetModel(nn.Module):
             ops.linear(h1, ly.w1, ly.bi, E.EPI_BIAS_GELU, out=mid)
             ops.linear(mid, ly.w2, ly.b2, E.EPI_BIAS, out=pre)
             ops.layernorm(pre, ly.g2, ly.b2n, pk.eps, resid=h1, out=h)       # LN(dense(mid) + h1)
+        if not pk.has_down:
+            ops.cast_f32(h, out=out.view(M, D))           # h.type(x.dtype) of the last hidden state (network.py:155-157)
+            return
         ops.linear(h, pk.dn1_w, pk.dn1_b, E.EPI_BIAS_TANH, out=h1)
         if split:
             ops.linear(h1, pk.dn2_w, pk.dn2_b, E.EPI_BIAS_SPLIT, out=out.view(M, 2 * D))

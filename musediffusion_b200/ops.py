@@ -92,6 +92,24 @@ def cast_bf16(x):
     return out
 
 
+def cast_f32(x, out=None):
+    """bf16 -> fp32 (md_cast_bf16_f32)."""
+    assert x.dtype == BF16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _cu(x, out)
+    K.cast_bf16_f32(x, out)
+    return out
+
+
+def add_pos_time(x, pos, temb, temb_stride, L, out):
+    """out = bf16((pos[l] + x) + temb[b]) for hidden_dim == hidden_size models (md_add_pos_time)."""
+    x = _c(x, torch.float32)
+    _cu(x, pos, temb, out)
+    K.add_pos_time(x, pos, temb, temb_stride, L, out)
+    return out
+
+
 def embed_gather(E, ids):
     E = _c(E, torch.float32)
     if ids.dtype not in (torch.int32, torch.int64):
