@@ -173,7 +173,7 @@ def golden_loop(fname, mode, seq_len, B, seed, diffusion_steps, step, strength=0
 
 
 def golden_loop_base(fname, mode, B, seed, diffusion_steps, step, strength=1.0, top_p=1, seq_len=2096,
-                     store_x_noised=None):
+                     store_x_noised=None, store_final=True):
     """BASELINE.json configs[0] / configs[2] at the base sequence length: the driver slice run/sample.py:177-220 on
     the unmodified reference, recording for EVERY rounding call (rounding.py:31-47, invoked at diffusion.py:322)
     the chosen ids and the top-2 squared-distance margin, so the GPU parity test can apply the north-star rule
@@ -235,7 +235,7 @@ def golden_loop_base(fname, mode, B, seed, diffusion_steps, step, strength=1.0, 
                         diffusion_steps=diffusion_steps, step=step, strength=strength, top_p=top_p,
                         input_ids=cond["input_ids"], input_mask=cond["input_mask"],
                         step_ids=np.stack(rec_ids), step_margin=np.stack(rec_margin),
-                        final_sample=sample.numpy(), tokens=tokens.numpy(),
+                        **({"final_sample": sample.numpy()} if store_final else {}), tokens=tokens.numpy(),
                         logit_margin=(top2[..., 0] - top2[..., 1]).numpy().astype(np.float32), **extra)
     print(fname, tokens.shape, len(rec_ids), "rounding calls, %.0f s" % (time.time() - t0), tokens[0, :20].tolist())
 
@@ -408,6 +408,15 @@ def main():
         torch.set_num_threads(os.cpu_count())
         golden_loop_base("loop_base_gen_ddpm24.npz", "generation", 2, 21, 24, 24)
         golden_loop_base("loop_base_mod_ddim100.npz", "modification", 2, 22, 2000, 100, strength=1.0)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "base_ddpm":
+        # the bench's own operating regime (BASELINE.json configs[1]): modification, 2000-step table, DDPM with truncated noise,
+        # rounding every step, the first 40 indices from the top of the chain (strength 0.02 -> t_enc = 40); ~4 min on 8 cores
+        import torch
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        golden_loop_base("loop_base_mod_ddpm40.npz", "modification", 2, 23, 2000, 2000, strength=0.02, store_x_noised=False,
+                         store_final=False)
         return
     import torch
     torch.manual_seed(0)
