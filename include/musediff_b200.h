@@ -105,7 +105,8 @@ int md_dist_scores(const float* x, const float* dot, const float* esq, float* ou
 /* Tensor-core versions of the two reductions above (tcgen05, split-bf16 operands x = xh + xl, E = Eh + El with the four
  * partial products accumulated in fp32: fp32-grade scores, the score matrix stays in TMEM).
  *   md_embed_split: once per embedding matrix.  E2 = bf16 [Vp, 2D] = [Eh | El], sqnorm = fp32 [Vp] = |E_v|^2 (+inf on
- *     the Vp - V padding rows), Vp = md_round_tc_padded_vocab(V).
+ *     the Vp - V padding rows), Vp = md_round_tc_padded_vocab(V); E_clamped (optional) = clamp(E, -1, 1), the rows
+ *     md_posterior_step gathers when clip_denoised follows the rounding (clip = 2 there).
  *   md_round_argmin_tc: mode 0: idx[m] = argmin_v (cst[v] - 2 x_m.E_v), cst = sqnorm  (rounding.py:21-28; |x_m|^2 is
  *     constant per row, the reference's clamp(dist, 0) only creates ties on bit-exact hits);
  *     mode 1: idx[m] = argmax_v (x_m.E_v + cst[v]), cst = lm_head bias padded with -inf  (network.py:91-93 + argmax).
@@ -115,7 +116,8 @@ int md_dist_scores(const float* x, const float* dot, const float* esq, float* ou
  * lo = bf16(x - hi)  (operand of the split-bf16 contractions: rounding, decode, get_logits). */
 int md_split_bf16(const float* x, void* out_bf16, int64_t rows, int D, int copies, cudaStream_t stream);
 int md_round_tc_padded_vocab(int V);
-int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, cudaStream_t stream);
+int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, float* E_clamped /* optional fp32 [V, D] */,
+                   cudaStream_t stream);
 int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x2_ws, int32_t* idx, float* margin,
                        int64_t M, int V, int D, int mode, cudaStream_t stream);
 
@@ -123,7 +125,8 @@ int md_round_argmin_tc(const float* x, const void* E2, const float* cst, void* x
  * x_{t-1} from x_t for mode DDPM (p_sample :349-404 with p_mean_variance :311-347, q_posterior_mean :257-278) or
  * DDIM (ddim_sample :701-757, _predict_eps_from_xstart :201-205):
  *   pred  = idx ? E[idx] : pred_in                      (denoised_fn_round, rounding.py:31-47)
- *   pred  = clip ? clamp(pred, -1, 1) : pred            (diffusion.py:323-324, AFTER rounding)
+ *   pred  = clip == 1 ? clamp(pred, -1, 1) : pred       (diffusion.py:323-324, AFTER rounding; clip == 2: E already holds
+ *                                                        clamp(E, -1, 1) — md_embed_split's E_clamped — nothing left to do)
  *   DDPM: x' = c1[t] pred + c2[t] x_t + [t != 0] exp(0.5 logvar[t]) n
  *   DDIM: eps = (sr[t] x_t - pred)/srm1[t]; sigma = eta sqrt((1-abp)/(1-ab)) sqrt(1-ab/abp);
  *         x' = pred sqrt(abp) + sqrt(1-abp-sigma^2) eps + [t != 0] sigma n

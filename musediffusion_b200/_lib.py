@@ -30,7 +30,7 @@ SIGNATURES = {
     "md_split_bf16": [c_p, c_p, c_i64, c_i, c_i, c_p],
     "md_dist_scores": [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_p],
     "md_round_tc_padded_vocab": [c_i],
-    "md_embed_split": [c_p, c_i, c_i, c_p, c_p, c_p],
+    "md_embed_split": [c_p, c_i, c_i, c_p, c_p, c_p, c_p],
     "md_round_argmin_tc": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_p],
     "md_posterior_step": [c_p, c_p, c_p, c_p, c_p, c_u64, c_u64, c_i64, c_p, c_i, c_p, c_i64, c_i64, c_p, c_p, c_p,
                           c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_f, c_p, c_p],

@@ -243,7 +243,7 @@ MD_DEVINL void step_counter_of(const StepArgs& a, uint32_t& lo, uint32_t& hi) {
     }
 }
 
-MD_DEVINL float clampf(float v, int clip) { return clip ? fminf(fmaxf(v, -1.0f), 1.0f) : v; }
+MD_DEVINL float clampf(float v, int clip) { return clip == 1 ? fminf(fmaxf(v, -1.0f), 1.0f) : v; }   // clip 2: rows pre-clamped
 
 // per-timestep scalars of one reverse step (computed once per thread when the whole batch shares t)
 struct StepCoef {
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const StepArgs a) {
 // Fast path for the shape the sampling loops actually use: D = 128 (one warp = one token row, lane = float4 column),
 // token-broadcast or absent mask, fewer than 2^24 tokens.  Four tokens per warp iteration, all loads first; addresses
 // are 32-bit and need no divisions (the per-sequence schedule index is only looked up when t is not shared).
-template <int MODE, int NOISE>
+template <int MODE, int NOISE, bool CLIP>
 __global__ void __launch_bounds__(256) posterior_step_d128_kernel(const StepArgs a) {
     const int lane = threadIdx.x & 31;
     const int M = a.B * a.L;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) posterior_step_d128_kernel(const StepArgs
             const uint32_t off = (uint32_t)tok * 128u + (uint32_t)lane * 4u;
             const StepCoef k = uniform_t ? ku : step_coef<MODE>(a.sched, a.t[tok / a.L], a.eta);
             float4 p = pr[u];
-            p.x = clampf(p.x, a.clip); p.y = clampf(p.y, a.clip); p.z = clampf(p.z, a.clip); p.w = clampf(p.w, a.clip);
+            if (CLIP) { p.x = clampf(p.x, 1); p.y = clampf(p.y, 1); p.z = clampf(p.z, 1); p.w = clampf(p.w, 1); }
             if (a.pred_out != nullptr) st_stream_f4(a.pred_out + off, p);
             const float sc = step_noise_scale<MODE>(k);
             // sigma == 0 (DDIM with eta = 0, or t == 0): the product sc * n is exactly 0 for any finite n -> skip the RNG
@@ -871,6 +871,7 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     if (D % 4 != 0) { set_last_error("md_posterior_step: D must be a multiple of 4"); return MD_ERR_ARG; }
     if ((idx == nullptr) == (pred_in == nullptr)) { set_last_error("md_posterior_step: exactly one of idx / pred_in"); return MD_ERR_ARG; }
     if (idx != nullptr && E == nullptr) { set_last_error("md_posterior_step: idx needs E"); return MD_ERR_ARG; }
+    if (clip == 2 && idx == nullptr) { set_last_error("md_posterior_step: clip = 2 (pre-clamped E) needs idx"); return MD_ERR_ARG; }
     if (mask != nullptr && x_start == nullptr) { set_last_error("md_posterior_step: mask needs x_start"); return MD_ERR_ARG; }
     if (mode != MD_STEP_DDPM && mode != MD_STEP_DDIM) { set_last_error("md_posterior_step: bad mode %d", mode); return MD_ERR_ARG; }
     if ((int64_t)B * L == 0) return MD_OK;
@@ -886,13 +887,14 @@ extern "C" __attribute__((visibility("default"))) int md_posterior_step(const fl
     const int nz = (noise != nullptr) ? 0 : (a.rng.central ? 1 : 2);
     if (D == 128 && (mask == nullptr || mask_d_stride == 0) && (int64_t)B * L < (1 << 24)) {
         const int g2 = ew_grid(((int64_t)B * L + kStepUnroll - 1) / kStepUnroll * 32, 256);
-#define MD_LAUNCH_FAST(MODE_)                                                                                     \
+#define MD_LAUNCH_FAST(MODE_, CLIP_)                                                                              \
     do {                                                                                                          \
-        if (nz == 0) posterior_step_d128_kernel<MODE_, 0><<<g2, 256, 0, stream>>>(a);                             \
-        else if (nz == 1) posterior_step_d128_kernel<MODE_, 1><<<g2, 256, 0, stream>>>(a);                        \
-        else posterior_step_d128_kernel<MODE_, 2><<<g2, 256, 0, stream>>>(a);                                     \
+        if (nz == 0) posterior_step_d128_kernel<MODE_, 0, CLIP_><<<g2, 256, 0, stream>>>(a);                      \
+        else if (nz == 1) posterior_step_d128_kernel<MODE_, 1, CLIP_><<<g2, 256, 0, stream>>>(a);                 \
+        else posterior_step_d128_kernel<MODE_, 2, CLIP_><<<g2, 256, 0, stream>>>(a);                              \
     } while (0)
-        if (mode == MD_STEP_DDPM) MD_LAUNCH_FAST(MD_STEP_DDPM); else MD_LAUNCH_FAST(MD_STEP_DDIM);
+        if (mode == MD_STEP_DDPM) { if (a.clip == 1) MD_LAUNCH_FAST(MD_STEP_DDPM, true); else MD_LAUNCH_FAST(MD_STEP_DDPM, false); }
+        else { if (a.clip == 1) MD_LAUNCH_FAST(MD_STEP_DDIM, true); else MD_LAUNCH_FAST(MD_STEP_DDIM, false); }
 #undef MD_LAUNCH_FAST
         return check_cuda(cudaGetLastError(), "posterior_step launch");
     }

@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     }
 }
 
-// E fp32 [V, D] -> E2 bf16 [Vp, 2D] = [hi | lo] (zero rows beyond V) and |E_v|^2 (fp32, +inf beyond V)
+// E fp32 [V, D] -> E2 bf16 [Vp, 2D] = [hi | lo] (zero rows beyond V), |E_v|^2 (fp32, +inf beyond V) and, optionally, the rows
+// clamped to [-1, 1] (what clip_denoised makes of a rounded x0, diffusion.py:323-324: the posterior kernel then gathers them
+// ready-made instead of clamping 128 values per token and step)
 __global__ void __launch_bounds__(128) embed_prepare_kernel(const float* __restrict__ E, __nv_bfloat16* __restrict__ E2,
-                                                            float* __restrict__ sqnorm, int V, int Vp, int D) {
+                                                            float* __restrict__ sqnorm, float* __restrict__ E_clamped, int V, int Vp, int D) {
     const int v = blockIdx.x;
     float s = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(128) embed_prepare_kernel(const float* __restr
         const __nv_bfloat16 h = __float2bfloat16_rn(e);
         E2[(size_t)v * 2 * D + d] = h;
         E2[(size_t)v * 2 * D + D + d] = __float2bfloat16_rn(e - __bfloat162float(h));
+        if (E_clamped != nullptr && v < V) E_clamped[(size_t)v * D + d] = fminf(fmaxf(e, -1.0f), 1.0f);
         s = fmaf(e, e, s);
     }
     __shared__ float red[4];
@@ -243,10 +246,10 @@ using namespace md;
 
 extern "C" __attribute__((visibility("default"))) int md_round_tc_padded_vocab(int V) { return (V + RT_BN - 1) / RT_BN * RT_BN; }
 
-extern "C" __attribute__((visibility("default"))) int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, cudaStream_t stream) {
+extern "C" __attribute__((visibility("default"))) int md_embed_split(const float* E, int V, int D, void* E2, float* sqnorm, float* E_clamped, cudaStream_t stream) {
     if (V <= 0 || D <= 0 || D % RT_BK != 0) { set_last_error("md_embed_split: D=%d must be a positive multiple of %d", D, RT_BK); return MD_ERR_ARG; }
     const int Vp = md_round_tc_padded_vocab(V);
-    embed_prepare_kernel<<<Vp, 128, 0, stream>>>(E, reinterpret_cast<__nv_bfloat16*>(E2), sqnorm, V, Vp, D);
+    embed_prepare_kernel<<<Vp, 128, 0, stream>>>(E, reinterpret_cast<__nv_bfloat16*>(E2), sqnorm, E_clamped, V, Vp, D);
     return check_cuda(cudaGetLastError(), "embed_split launch");
 }
 

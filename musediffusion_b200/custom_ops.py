@@ -112,8 +112,8 @@ def _dist_scores(x, dot, esq, out):
     launch("md_dist_scores", _p(x), _p(dot), _p(esq), _p(out), out.shape[0], out.shape[1], dot.shape[1], x.shape[-1], _stream())
 
 
-def _embed_split(E, E2, sqnorm):
-    launch("md_embed_split", _p(E), E.shape[0], E.shape[1], _p(E2), _p(sqnorm), _stream())
+def _embed_split(E, E2, sqnorm, E_clamped):
+    launch("md_embed_split", _p(E), E.shape[0], E.shape[1], _p(E2), _p(sqnorm), _p(E_clamped), _stream())
 
 
 def _round_argmin_tc(x, E2, cst, ws, idx, margin, V, mode):
@@ -184,13 +184,13 @@ _define("attention_bf16(Tensor qkv, Tensor(a!) out, int B, int L, int NH) -> ()"
 _define("round_argmin(Tensor x, Tensor E, Tensor(a!) idx, Tensor(b!)? margin) -> ()", _round_argmin)
 _define("logits_argmax(Tensor x, Tensor E, Tensor bias, Tensor(a!) tok, Tensor(b!)? margin) -> ()", _logits_argmax)
 _define("split_bf16(Tensor x, Tensor(a!) out, int copies) -> ()", _split_bf16)
-_define("embed_split(Tensor E, Tensor(a!) E2, Tensor(b!) sqnorm) -> ()", _embed_split)
+_define("embed_split(Tensor E, Tensor(a!) E2, Tensor(b!) sqnorm, Tensor(c!)? E_clamped) -> ()", _embed_split)
 _define("dist_scores(Tensor x, Tensor dot, Tensor esq, Tensor(a!) out) -> ()", _dist_scores)
 _define("round_argmin_tc(Tensor? x, Tensor E2, Tensor cst, Tensor(a!) ws, Tensor(b!) idx, Tensor(c!)? margin, int V, int mode) -> ()",
         _round_argmin_tc)
 _define("posterior_step(Tensor x_t, Tensor? idx, Tensor? pred, Tensor? E, Tensor? noise, int seed, int step_counter, int seq_offset, "
         "Tensor t, int t_stride, Tensor? mask, int mask_tok_stride, int mask_d_stride, Tensor? x_start, Tensor(a!) out, "
-        "Tensor(b!)? out_bf16, Tensor(c!)? pred_out, Tensor(d!)? mean_out, int mode, float eta, bool clip, float top_p, "
+        "Tensor(b!)? out_bf16, Tensor(c!)? pred_out, Tensor(d!)? mean_out, int mode, float eta, int clip, float top_p, "
         "Tensor? step_counter_dev) -> ()", _posterior_step)
 _define("xstart_from_eps(Tensor x_t, Tensor eps, Tensor t, int t_stride, Tensor(a!) out) -> ()", _xstart_from_eps)
 _define("q_sample(Tensor x0, Tensor? noise, int seed, int step_counter, int seq_offset, Tensor? t, int t_stride, Tensor? mask, "

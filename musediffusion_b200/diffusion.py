@@ -394,6 +394,8 @@ class GaussianDiffusion:
         ctr_base = self._noise_calls + 1                # the value _next_counter() hands to the first step of an eager loop
         seed = self._seed()
         se = ops.split_embedding(E)
+        # clip_denoised after rounding = gathering rows of clamp(E, -1, 1): built once per embedding matrix, not per token and step
+        E_step, clip_step = (se.E_clamped, 2) if clip_denoised else (E, 0)
         idx = torch.empty((x.shape[0] * x.shape[1],), dtype=torch.int32, device=dev)
         if mode == _lib.STEP_DDPM:
             tp = top_p if (top_p is not None and top_p > 0) else 0.0
@@ -410,8 +412,8 @@ class GaussianDiffusion:
                 if not self.predict_xstart:
                     out = ops.xstart_from_eps(x, out, t_cur)
                 ops.round_argmin_tc(out, se, out=idx)
-            ops.posterior_step(x, t_cur, mode, idx=idx, E=E, seed=seed, seq_offset=self.seq_offset, mask=mask, x_start=x_start,
-                               eta=eta, clip=clip_denoised, top_p=tp, out=x, out_bf16=xb, step_counter_dev=ctr_cur)
+            ops.posterior_step(x, t_cur, mode, idx=idx, E=E_step, seed=seed, seq_offset=self.seq_offset, mask=mask, x_start=x_start,
+                               eta=eta, clip=clip_step, top_p=tp, out=x, out_bf16=xb, step_counter_dev=ctr_cur)
 
         graph, nodes = None, 0
         for k, i in enumerate(indices):

@@ -229,8 +229,9 @@ class SplitEmbedding:
         self.Vp = _lib.lib.md_round_tc_padded_vocab(self.V)
         self.E2 = torch.empty((self.Vp, 2 * self.D), dtype=BF16, device=E.device)
         self.sqnorm = torch.empty((self.Vp,), dtype=torch.float32, device=E.device)
+        self.E_clamped = torch.empty_like(E)      # clamp(E, -1, 1): what clip_denoised makes of a rounded x0 (diffusion.py:323-324)
         _cu(E)
-        K.embed_split(E, self.E2, self.sqnorm)
+        K.embed_split(E, self.E2, self.sqnorm, self.E_clamped)
         self._ws = {}
 
     def logit_cst(self, bias):
@@ -311,6 +312,7 @@ def _t_args(t, B):
 def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0, step_counter=0, seq_offset=0,
                    mask=None, x_start=None, eta=0.0, clip=True, top_p=0.0, out=None, out_bf16=None, pred_out=None,
                    mean_out=None, step_counter_dev=None):
+    """clip: False / True as diffusion.py:323-324, or 2 = `E` already holds clamp(E, -1, 1) (SplitEmbedding.E_clamped)."""
     x_t = _c(x_t, torch.float32)
     B, L, D = x_t.shape
     t, t_stride = _t_args(t, B)
@@ -329,7 +331,7 @@ def posterior_step(x_t, t, mode, idx=None, pred=None, E=None, noise=None, seed=0
         raise _lib.MuseDiffLibraryError("md_posterior_step: exactly one of idx / pred_in")
     _cu(x_t, idx, pred, E, noise, t, mask_t, x_start, out, out_bf16, pred_out, mean_out, step_counter_dev)
     K.posterior_step(x_t, idx, pred, E, noise, _s64(seed), _s64(step_counter), int(seq_offset), t, t_stride, mask_t, ts, ds, x_start,
-                     out, out_bf16, pred_out, mean_out, mode, float(eta), bool(clip), float(top_p or 0.0), step_counter_dev)
+                     out, out_bf16, pred_out, mean_out, mode, float(eta), int(clip), float(top_p or 0.0), step_counter_dev)
     return out
 
 

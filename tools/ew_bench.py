@@ -44,6 +44,9 @@ def rep(name, ms, nbytes):
 
 ms = timeit(lambda: ops.posterior_step(x, t, _lib.STEP_DDPM, idx=idx, E=E, seed=1, step_counter=3, mask=mask, x_start=xs, top_p=1.0, out=out, out_bf16=xb))
 rep("posterior DDPM philox top_p=1 (+bf16 copy)", ms, M * (512 + 4 + 512 + 256))
+Ec = ops.SplitEmbedding(E).E_clamped
+ms = timeit(lambda: ops.posterior_step(x, t, _lib.STEP_DDPM, idx=idx, E=Ec, seed=1, step_counter=3, mask=mask, x_start=xs, top_p=1.0, clip=2, out=out, out_bf16=xb))
+rep("  ... gathering pre-clamped rows (the loop's path)", ms, M * (512 + 4 + 512 + 256))
 ms = timeit(lambda: ops.posterior_step(x, t, _lib.STEP_DDPM, idx=idx, E=E, noise=noise, mask=mask, x_start=xs, out=out, out_bf16=xb))
 rep("posterior DDPM external noise", ms, M * (512 + 4 + 512 + 512 + 256))
 ms = timeit(lambda: ops.posterior_step(x, t, _lib.STEP_DDIM, idx=idx, E=E, seed=1, step_counter=3, mask=mask, x_start=xs, out=out, out_bf16=xb))
