@@ -540,27 +540,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             mbar_wait_a<true>(sb + SB_O_FULL, ocnt & 1);
             ++ocnt;
             tc_fence_after();
-            if (wk.mode == ITEM_SPLIT && x == 1) {
-                // hand (m, l) to stream 0, which also reads this stream's O straight from TMEM (same lane quadrant)
-                sXchg[r] = st.m_used;
-                sXchg[128 + r] = st.l_sum;
-                tc_fence_before();
-                asm volatile("bar.sync 2, 256;" ::: "memory");       // (m, l) visible, O1 complete
-                asm volatile("bar.sync 3, 256;" ::: "memory");       // stream 0 has read O1
-                mbar_arrive_a(sb + SB_O_EMPTY);
-                continue;
-            }
             uint32_t o[2][32];
             float scale;
             if (wk.mode == ITEM_SPLIT) {
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                // Stream 1 hands (m, l) to stream 0, which also reads stream 1's O straight from TMEM (both warpgroups address
+                // the same lane quadrants).  Both warpgroups pass through the SAME two bar.sync instructions (compute-sanitizer's
+                // synccheck rejects one named barrier reached at two program counters), and both execute the merge arithmetic:
+                // a register array defined under a predicate would be live around the whole work-item loop for ptxas
+                // (64 registers spilled per key block); stream 1 discards its copy.
+                if (x == 1) {
+                    sXchg[r] = st.m_used;
+                    sXchg[128 + r] = st.l_sum;
+                }
+                tc_fence_before();
+                asm volatile("bar.sync 2, 256;" ::: "memory");       // (m, l) visible, O1 complete
                 tc_fence_after();
                 const float m1 = sXchg[r], l1 = sXchg[128 + r];
                 const float m = fmaxf(st.m_used, m1);
                 const float w0 = fast_exp2(st.m_used - m), w1 = fast_exp2(m1 - m);
                 scale = 1.0f / (st.l_sum * w0 + l1 * w1);
-                // (always executed, also by warps whose rows do not exist: a register written under one predicate and read
-                // under another stays live around the whole work-item loop in ptxas' eyes and spills 64 registers)
                 uint32_t o1[2][32];
                 tmem_ld32(tO, o[0]);
                 tmem_ld32(tO + 32, o[1]);
@@ -573,8 +571,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     for (int c = 0; c < 32; ++c)
                         o[g][c] = __float_as_uint(fmaf(__uint_as_float(o[g][c]), w0, __uint_as_float(o1[g][c]) * w1));
                 tc_fence_before();
-                asm volatile("bar.sync 3, 256;" ::: "memory");
+                asm volatile("bar.sync 3, 256;" ::: "memory");       // stream 0 has read O1
                 mbar_arrive_a(sb + SB_O_EMPTY);
+                if (x == 1) continue;
             } else {
                 scale = 1.0f / st.l_sum;
                 tmem_ld32(tO, o[0]);
@@ -632,9 +631,9 @@ extern "C" __attribute__((visibility("default"))) int md_attention_bf16(const vo
     if (int e = make_tmap_bf16_3d(&tmo, out, H, L, B, H, (uint64_t)L * H, 64, 128)) return e;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const AttArgs);
     // tuning switch: MD_ATT_POLY = how many of every 8 element pairs compute 2^x on the FMA pipe instead of the MUFU.
-    // Alone at full clock 3 is fastest (4.39 ms at B = 256 against 4.58 for 2 and ~5 for 0), but inside the power-capped
-    // step the clock is set by the energy of the whole step and the variant with the fewest instructions (0: MUFU only)
-    // gives the shortest step and the shortest in-step attention time (profiles/r2_attention_ab.md) -> default 0
+    // Alone at full clock 0 and 3 are fastest (4.39-4.44 ms at B = 256 against 4.58 for 2); inside the power-capped step
+    // the clock is set by the energy of the whole step and the variant with the fewest instructions (0: MUFU only) gives
+    // the shortest in-step attention time (profiles/r2_attention_ab.md) -> default 0
     static const int poly = env_int("MD_ATT_POLY", 0);
     static const KernelFn kern = trace_ptr != nullptr ? attention_kernel<2, true>
                                  : poly == 9 ? attention_kernel<9> : poly >= 4 ? attention_kernel<4> : poly == 3 ? attention_kernel<3>
