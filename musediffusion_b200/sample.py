@@ -121,6 +121,8 @@ def create_parser():
             sp.add_argument("--num_batches", type=int, default=1)
         else:
             sp.add_argument("--num_samples", type=int, default=1000)
+            from .meta import add_meta_arguments
+            add_meta_arguments(sp)                       # config/sample.py:223-230: --bpm ... --chord_progression / --meta_json
     return p
 
 
@@ -148,9 +150,16 @@ def main(argv=None):
     model, diffusion, targs = load_model(args.model_path, dev)
     model_emb = build_model_emb(model, dev)
     seed_all(args.sample_seed, deterministic=True)
+    midi_meta = None
+    if args.mode == "generation":
+        from .meta import meta_from_args, meta_to_batch
+        midi_meta = meta_from_args(args)
     if args.input_npz:
         data = np.load(args.input_npz)
         ids_all, mask_all = data["input_ids"], data["input_mask"]
+    elif midi_meta is not None:                                   # run/sample.py:117-121: every sample from the one meta
+        b = meta_to_batch(midi_meta, args.num_samples, targs.seq_len)
+        ids_all, mask_all = b["input_ids"].numpy(), b["input_mask"].numpy()
     else:
         from .synthetic import make_synthetic_batch
         n = args.num_samples if args.mode == "generation" else args.batch_size * args.num_batches

@@ -300,6 +300,63 @@ def golden_meta_prefix():
     print("meta_batch.npz", b["input_ids"][0, :30].tolist())
 
 
+def meta_encode_cases(n=60, seed=9):
+    """Seeded meta dicts over every category table (+ chord progressions with in-bar changes and 'NN')."""
+    import random as _r
+    from commu.preprocessor.utils import constants as C
+    from commu.preprocessor.encoder.event_tokens import base_event
+    rng = _r.Random(seed)
+    chords = [k[6].upper() + k[7:] for k in base_event if k.startswith("Chord_")]
+    cases = []
+    for i in range(n):
+        bars = rng.choice([1, 2, 4, 8, 16])
+        prog, cur = [], rng.choice(chords)
+        for _ in range(bars * 8):
+            if rng.random() < 0.25:
+                cur = rng.choice(chords)
+            prog.append(cur)
+        cases.append({"bpm": rng.choice([0, 3, 5, 37, 70, 120, 199, 200, 201, 400]), "audio_key": rng.choice(list(C.KEY_MAP)),
+                      "time_signature": rng.choice(list(C.TIME_SIG_MAP)), "pitch_range": rng.choice(list(C.PITCH_RANGE_MAP)),
+                      "num_measures": rng.choice([4, 4.5, 5, 8, 8.9, 9, 16, 17]), "inst": rng.choice(list(C.INST_MAP)),
+                      "genre": rng.choice(list(C.GENRE_MAP)), "min_velocity": rng.randrange(0, 128),
+                      "max_velocity": rng.randrange(0, 128), "track_role": rng.choice(list(C.TRACK_ROLE_MAP)),
+                      "rhythm": rng.choice(list(C.RHYTHM_MAP)), "chord_progression": "-".join(prog)})
+    return cases
+
+
+def golden_meta_encode():
+    """tests/golden/meta_encode.json: MetaToSequence.execute (utils/decode_util.py:44-47) on seeded meta dicts; the
+    per-field "unknown" tokens and the error cases through commu's encode_meta on a plain attribute object (pydantic
+    would reject "unknown" for the int fields before the encoder sees it)."""
+    import json
+    from types import SimpleNamespace
+    from MuseDiffusion.utils.decode_util import MetaToSequence
+    from commu.preprocessor.encoder.meta import encode_meta, META_ENCODING_ORDER
+    from commu.preprocessor.utils.exceptions import UnprocessableMidiError
+    m2s = MetaToSequence()
+    cases = meta_encode_cases()
+    out = {"cases": [{"meta": c, "tokens": [int(t) for t in m2s.execute(c)]} for c in cases], "unknown": [], "errors": []}
+    base = {k: v for k, v in cases[0].items() if k != "chord_progression"}
+    for name in META_ENCODING_ORDER:
+        d = dict(base)
+        d[name] = "unknown"
+        try:
+            out["unknown"].append({"field": name, "tokens": [int(t) for t in encode_meta(SimpleNamespace(**d))]})
+        except UnprocessableMidiError:
+            out["errors"].append({"field": name, "value": "unknown"})
+    for name, bad in (("audio_key", "hmajor"), ("num_measures", 7), ("num_measures", 32), ("inst", "kazoo"),
+                      ("time_signature", "5/4"), ("rhythm", "swing")):
+        d = dict(base)
+        d[name] = bad
+        try:
+            encode_meta(SimpleNamespace(**d))
+            raise SystemExit("expected an error for %s=%s" % (name, bad))
+        except UnprocessableMidiError:
+            out["errors"].append({"field": name, "value": bad})
+    json.dump(out, open(os.path.join(OUT, "meta_encode.json"), "w"), indent=0)
+    print("meta_encode.json", len(out["cases"]), "cases,", len(out["unknown"]), "unknown,", len(out["errors"]), "errors")
+
+
 def golden_decode_prepare():
     """the reference's own SequenceToMidi (decode_util.py:57-199) on the rows above."""
     from MuseDiffusion.utils.decode_util import SequenceToMidi, SequenceToMidiError
@@ -379,6 +436,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         golden_metrics()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "meta":
+        golden_meta_encode()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         golden_decode_prepare()
         return
@@ -424,6 +484,7 @@ def main():
     golden_schedules()
     golden_rounding()
     golden_meta_prefix()
+    golden_meta_encode()
     golden_forward(64, 2, 1, "forward_tiny.npz", [999.5, 3.0])
     golden_forward(200, 1, 2, "forward_ragged.npz", [500.0])          # L not a multiple of 64/128
     golden_forward(2096, 1, 4, "forward_base.npz", [250.0])           # the base-config shape
