@@ -5,15 +5,18 @@ The reference walks the sampled batch row by row in Python, rank after rank (`ru
 through `SequenceToMidi.decode` (:207-214) = split_meta_midi + remove_padding + restore_chord + validate_* and only
 then to the MIDI writer.  Here the whole batch takes one kernel launch (`md_decode_prepare`); what comes back is, per
 row, the reference's outcome (OK or the text of the SequenceToMidiError it would raise), the restored note sequence
-and the 11 meta tokens — exactly the two arrays `decode_event_sequence` (:201-205) needs.  Writing MIDI files stays
-with the reference (`miditoolkit` is not part of this path).
+and the 11 meta tokens — exactly the two arrays `decode_event_sequence` (:201-205) needs.  `decode_batch` then turns
+every valid row into a MIDI file through `midi.py` (vectorised event walk + a Standard-MIDI-File writer; `miditoolkit`
+is not needed), with the reference's file names, warnings and summaries.
 """
+import os
+
 from collections import namedtuple
 
 import numpy as np
 import torch
 
-from . import ops
+from . import midi, ops
 
 OK, NO_EOS, RESTORE_FAILED, VALIDATION_FAILED, STRICT_FAILED, INDEX_ERROR, TOO_LONG = range(7)
 STATUS_TEXT = {
@@ -68,3 +71,52 @@ def report_failures(prepared, batch_index, previous_count, print_fn=print):
                              % (index, batch_index))
         print_fn("<Warning> Batch %d Index %d (Original: %d) - Generation Failure: %s"
                  % (batch_index, index, previous_count + index, STATUS_TEXT[code]))
+
+
+def decode_batch(mode, sequences, input_ids_mask_ori, batch_index, previous_count, output_dir, return_indices=False,
+                 strict_validation=False, prepared=None):
+    """`decode_batch` (decode_util.py:233-257) with both writers behind it: modification keeps the original index in the
+    file name and reports every failure (`batch_decode_seq2seq`, :260-331); generation numbers the VALID files
+    consecutively from `previous_count` and skips failures quietly (`batch_decode_generation`, :334-384).  Rows the
+    reference would abort on (IndexError inside its validation) raise here too.  Returns valid_count, or
+    (valid_count, invalid_idxes) with return_indices.  `prepared` (not in the reference): a PreparedBatch the caller already
+    holds for these rows."""
+    if mode not in ("generation", "modification"):
+        raise AssertionError("Unknown decoding mode")
+    prep = prepared if prepared is not None else prepare_batch(sequences, input_ids_mask_ori, strict_validation=strict_validation)
+    n, valid_index = len(prep.status), previous_count
+    for index in range(n):
+        code = int(prep.status[index])
+        if code == INDEX_ERROR:
+            raise IndexError("row %d of batch %d: the reference's decode aborts here (index out of range while validating)"
+                             % (index, batch_index))
+        if code != OK:
+            if mode == "modification":
+                print("<Warning> Batch %d Index %d (Original: %d) - Generation Failure: %s"
+                      % (batch_index, index, previous_count + index, STATUS_TEXT[code]))
+            continue
+        decoded = midi.decode_event_sequence(prep.note_seqs[index], prep.metas[index])
+        log = " ".join("OOV: %d" % w for w in decoded.oov)
+        if mode == "modification":
+            if log:
+                print("<Warning> Batch %d Index %d (Original: %d) - %s" % (batch_index, index, previous_count + index, log))
+            name = "%07d_batch%05d_%04d.midi" % (previous_count + index, batch_index, index)
+        else:
+            if log:
+                print("<Warning> Index %d - %s" % (valid_index, log))
+            name = "generated_%07d.midi" % valid_index
+        decoded.dump(os.path.join(output_dir, name))
+        valid_index += 1
+    valid_count = valid_index - previous_count
+    if mode == "modification":
+        print("\n" + (" Summary of Batch %d " % batch_index).center(60, "=") + "\n"
+              " * Original index: from %d to %d\n * %d valid sequences are converted to midi into path:\n     %s\n"
+              " * %d sequences are invalid.\n" % (previous_count, previous_count + n, valid_count, os.path.abspath(output_dir),
+                                                 len(prep.invalid_idxes))
+              + (" * Index (in batch %d) of invalid sequence:\n    %s\n" % (batch_index, prep.invalid_idxes)
+                 if prep.invalid_idxes else "") + "=" * 60 + "\n")
+    else:
+        print("\n" + (" Summary of Trial %d " % batch_index).center(60, "=") + "\n"
+              " * %d valid sequences are converted to midi into path:\n     %s\n * Totally %d sequences are converted.\n"
+              % (valid_count, os.path.abspath(output_dir), valid_index) + "=" * 60 + "\n")
+    return (valid_count, prep.invalid_idxes) if return_indices else valid_count

@@ -191,21 +191,17 @@ def main(argv=None):
                 n = min(args.batch_size, len(ids_all) - (base + k) * args.batch_size)
                 rows.append((base + k, gathered[k, :n]))
     if rank == 0:
-        # token-level half of decode_batch (utils/decode_util.py:233-384): one launch per batch on the gathered ids
+        # decode_batch (utils/decode_util.py:233-384) on the gathered ids: one launch per batch for the token-level half, then one
+        # MIDI file per valid row, named and numbered like the reference's
         flat, statuses, valid = [], [], 0
         for bi, tok in rows:
             mask = torch.from_numpy(mask_all[bi * args.batch_size: bi * args.batch_size + tok.shape[0]]).to(dev)
             prep = decode_util.prepare_batch(tok, mask, strict_validation=args.strict_validation)
-            st = prep.status
             flat.append(tok.cpu().numpy().astype(np.int64))
-            statuses.append(st)
-            for index in np.nonzero(st != decode_util.OK)[0]:         # same warnings / counts as batch_decode_* prints
-                print("<Warning> Batch %d Index %d (Original: %d) - Generation Failure: %s"
-                      % (bi, index, bi * args.batch_size + index, decode_util.STATUS_TEXT[int(st[index])]))
-            for index in np.nonzero(st == decode_util.OK)[0]:         # what decode_event_sequence (:201-205) would be handed
-                np.savez(os.path.join(out_dir, "%07d_batch%05d_%04d.notes.npz" % (bi * args.batch_size + index, bi, index)),
-                         note_seq=prep.note_seqs[index], encoded_meta=prep.metas[index])
-            valid += int((st == decode_util.OK).sum())
+            statuses.append(prep.status)
+            valid += decode_util.decode_batch(args.mode, tok, mask, batch_index=bi, output_dir=out_dir,
+                                              previous_count=valid if args.mode == "generation" else bi * args.batch_size,
+                                              strict_validation=args.strict_validation, prepared=prep)
         np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
         np.save(os.path.join(out_dir, "decode_status.npy"), np.concatenate(statuses))
         print("### Total takes %.2fs; %d sequences (%d valid) -> %s"

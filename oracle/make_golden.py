@@ -386,6 +386,115 @@ def golden_decode_prepare():
     np.savez_compressed(os.path.join(OUT, "decode_prepare.npz"), tokens=tokens, masks=masks, **out)
 
 
+def _recording_miditoolkit():
+    """miditoolkit is absent here: give the reference's write_midi (commu/preprocessor/encoder/encoder_utils.py:386-497)
+    plain containers that keep what they are handed, so its event walk runs unmodified and its output can be read back."""
+    import sys as _sys
+    from types import SimpleNamespace as NS
+    mt = _sys.modules["miditoolkit"]
+
+    def rec(kind, *names):
+        def make(*a, **k):
+            d = dict(zip(names, a))
+            d.update(k)
+            return NS(kind=kind, **d)
+        return make
+
+    class MidiFile:
+        def __init__(self, *a, **k):
+            self.time_signature_changes, self.key_signature_changes, self.tempo_changes = [], [], []
+            self.instruments, self.markers, self.ticks_per_beat = [], [], None
+    mt.Note = rec("note", "velocity", "pitch", "start", "end")
+    mt.KeySignature = rec("key", "key_name", "time")
+    mt.MidiFile = MidiFile
+    mt.midi.parser.MidiFile = MidiFile
+    c = mt.midi.containers
+    c.TimeSignature = rec("ts", "numerator", "denominator", "time")
+    c.TempoChange = rec("tempo", "tempo", "time")
+    c.Marker = rec("marker", "text", "time")
+
+    def instrument(program, is_drum=False, name=""):
+        return NS(kind="inst", program=program, is_drum=is_drum, name=name, notes=[])
+    c.Instrument = instrument
+
+
+def golden_midi_decode():
+    """tests/golden/midi_decode.json: the reference's decode_event_sequence (utils/decode_util.py:201-205 ->
+    EventSequenceEncoder.decode -> write_midi) on every row of decode_cases() that passes validate_once, with the OOV lines
+    it prints; rows on which it raises keep the exception's class name."""
+    import contextlib
+    import io
+    import json
+    from MuseDiffusion.utils.decode_util import SequenceToMidi, SequenceToMidiError
+    from decode_oracle import decode_cases
+    _recording_miditoolkit()
+    tokens, masks = decode_cases()
+    dec = SequenceToMidi(strict_validation=False)
+    rows = []
+    for b in range(len(tokens)):
+        try:
+            ns, mt = dec.split_meta_midi(tokens[b], masks[b])
+            dec.validate_generated_sequence(ns)
+        except (SequenceToMidiError, IndexError):
+            continue
+        log = io.StringIO()
+        row = {"row": b}
+        try:
+            with contextlib.redirect_stdout(log):
+                midi = dec.decode_event_sequence(ns, mt)
+        except Exception as exc:                                   # e.g. KeyError for an "unknown" key / time-signature token
+            row["error"] = exc.__class__.__name__
+        else:
+            inst, = midi.instruments
+            row.update(ticks_per_beat=int(midi.ticks_per_beat), program=int(inst.program), is_drum=bool(inst.is_drum),
+                       tempo=[[int(t.tempo), int(t.time)] for t in midi.tempo_changes],
+                       time_signature=[[int(t.numerator), int(t.denominator), int(t.time)] for t in midi.time_signature_changes],
+                       key=[[k.key_name, int(k.time)] for k in midi.key_signature_changes],
+                       notes=[[int(n.velocity), int(n.pitch), int(n.start), int(n.end)] for n in inst.notes],
+                       markers=[[m.text, int(m.time)] for m in midi.markers], oov=log.getvalue().splitlines())
+        rows.append(row)
+    # direct cases: valid meta over every time signature / key, long note sequences, chords, OOV words, broken groups
+    rng = np.random.default_rng(77)
+    direct = []
+    for k in range(48):
+        mt = np.array([int(rng.integers(561, 601)), int(rng.integers(602, 626)), 627 + k % 4, int(rng.integers(631, 638)),
+                       int(rng.integers(638, 641)), int(rng.integers(642, 650)), int(rng.integers(651, 653)),
+                       int(rng.integers(654, 719)), int(rng.integers(654, 719)), int(rng.integers(720, 726)),
+                       int(rng.integers(727, 729))])
+        ns = []
+        for _ in range(int(rng.integers(1, 9))):
+            ns.append(2)
+            for _ in range(int(rng.integers(0, 12))):
+                u = rng.random()
+                if u < 0.70:
+                    ns += [int(rng.integers(432, 560)), int(rng.integers(131, 195)), int(rng.integers(3, 131)), int(rng.integers(304, 432))]
+                elif u < 0.85:
+                    ns += [int(rng.integers(432, 560)), int(rng.integers(195, 304))]
+                elif u < 0.92:
+                    ns.append(int(rng.choice([0, 560, 600, 650, 728, 1000])))          # words outside the event vocabulary
+                else:
+                    ns += [int(rng.integers(432, 560)), int(rng.integers(131, 195))]   # a group cut short
+        if k % 3 == 0:
+            ns = ns[1:]                                                                 # sequence that does not open with Bar
+        ns.append(1)
+        ns = np.array(ns)
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            midi = dec.decode_event_sequence(ns, mt)
+        inst, = midi.instruments
+        direct.append(dict(note_seq=ns.tolist(), meta=mt.tolist(), ticks_per_beat=int(midi.ticks_per_beat),
+                           tempo=[[int(t.tempo), int(t.time)] for t in midi.tempo_changes],
+                           time_signature=[[int(t.numerator), int(t.denominator), int(t.time)] for t in midi.time_signature_changes],
+                           key=[[kk.key_name, int(kk.time)] for kk in midi.key_signature_changes],
+                           notes=[[int(n.velocity), int(n.pitch), int(n.start), int(n.end)] for n in inst.notes],
+                           markers=[[m.text, int(m.time)] for m in midi.markers], oov=log.getvalue().splitlines()))
+    json.dump({"rows": rows, "direct": direct}, open(os.path.join(OUT, "midi_decode.json"), "w"))
+    print("direct:", len(direct), "cases,", sum(len(r["notes"]) for r in direct), "notes,", sum(len(r["markers"]) for r in direct),
+          "markers,", sum(len(r["oov"]) for r in direct), "OOV lines")
+    print("midi_decode.json", len(rows), "rows,", sum("error" in r for r in rows), "errors,",
+          sum(len(r.get("notes", ())) for r in rows), "notes,", sum(bool(r.get("oov")) for r in rows), "rows with OOV")
+
+
 def golden_merge_and_mask(seq_len=96):
     """the reference's own helper_tokenize (data/preprocess.py:26-70), helper_filter
     (:73-81) and collate_batches (data/wrapper.py:90-126) on the rows of preprocess_oracle.merge_cases()."""
@@ -442,6 +551,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         golden_decode_prepare()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "midi":
+        golden_midi_decode()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "merge":
         golden_merge_and_mask()
         return
@@ -494,6 +606,7 @@ def main():
     golden_loop("loop_mod_ddim.npz", "modification", 64, 2, 13, 2000, 20, strength=1.0)
     golden_loop("loop_gen_ddim.npz", "generation", 96, 2, 14, 2000, 10)
     golden_decode_prepare()
+    golden_midi_decode()
     golden_merge_and_mask()
     golden_metrics()
     golden_training_args()

@@ -97,7 +97,7 @@ def test_rejects_cpu_tensors_and_bad_shapes():
 
 def test_cli_generation_end_to_end(tmp_path, capsys):
     """`python -m musediffusion_b200 generation ...` on a small random-init checkpoint (2-layer encoder, seq_len 64):
-    checkpoint + training_args.json in, tokens.npy + decode_status.npy out, failure warnings worded like the reference."""
+    checkpoint + training_args.json in, tokens.npy + decode_status.npy + generated_*.midi out, summaries worded like the reference."""
     import json
     from musediffusion_b200 import sample
     from musediffusion_b200.initialization import create_model_and_diffusion
@@ -122,5 +122,42 @@ def test_cli_generation_end_to_end(tmp_path, capsys):
     want = D.decode_prepare_batch(tokens, b["input_mask"], True)
     assert np.array_equal(status, want[0])
     printed = capsys.readouterr().out
-    assert printed.count("Generation Failure") == int((status != 0).sum())
+    assert "Generation Failure" not in printed            # generation skips failures quietly (decode_util.py:357-359)
+    assert printed.count("Summary of Trial") == 2
     assert "(%d valid)" % int((status == 0).sum()) in printed
+    assert sorted(f for f in os.listdir(d) if f.endswith(".midi")) == ["generated_%07d.midi" % k for k in range(int((status == 0).sum()))]
+
+
+@pytest.mark.parametrize("mode", ["modification", "generation"])
+def test_decode_batch_writes_the_midi_files_of_the_reference(tmp_path, golden_dir, capsys, mode):
+    """decode_batch (utils/decode_util.py:233-384): rows of the decode fixture -> files named / numbered as the reference's
+    two writers do, each holding the notes the reference's write_midi produced (tests/golden/midi_decode.json)."""
+    import json
+    from musediffusion_b200 import midi
+    g = np.load(os.path.join(golden_dir, "decode_prepare.npz"))
+    gold = {r["row"]: r for r in json.load(open(os.path.join(golden_dir, "midi_decode.json")))["rows"]}
+    good = [b for b, r in gold.items() if "error" not in r]
+    bad = [b for b in range(len(g["status_0"])) if g["status_0"][b] in (1, 2, 3)][:7]
+    rows = sorted(good[:20] + bad)
+    valid, invalid = decode_util.decode_batch(mode, g["tokens"][rows], g["masks"][rows], batch_index=3, previous_count=60,
+                                              output_dir=str(tmp_path), return_indices=True)
+    assert valid == 20 and invalid == [k for k, b in enumerate(rows) if b in bad]
+    printed = capsys.readouterr().out
+    k_valid = 0
+    for k, b in enumerate(rows):
+        if b in bad:
+            continue
+        name = "%07d_batch%05d_%04d.midi" % (60 + k, 3, k) if mode == "modification" else "generated_%07d.midi" % (60 + k_valid)
+        k_valid += 1
+        tpb, (conductor, track) = midi.read_smf((tmp_path / name).read_bytes())
+        ons = sorted((t, raw[0], raw[1]) for t, st, raw in track if st == 0x90)
+        assert ons == sorted((s, p, v) for v, p, s, e in gold[b]["notes"])
+        assert [[raw.decode(), t] for t, kind, raw in conductor if kind == (0xFF, 0x06)] == sorted(gold[b]["markers"], key=lambda m: m[1])
+    assert len(os.listdir(tmp_path)) == 20
+    if mode == "modification":
+        assert printed.count("Generation Failure") == len(bad) and "Summary of Batch 3" in printed and " * 7 sequences are invalid." in printed
+    else:
+        assert "Generation Failure" not in printed and "Summary of Trial 3" in printed and " * Totally 80 sequences are converted." in printed
+    raising = [b for b, r in gold.items() if "error" in r][:1]
+    with pytest.raises(KeyError):                         # an "unknown" key / time-signature token aborts the reference too
+        decode_util.decode_batch(mode, g["tokens"][raising], g["masks"][raising], 0, 0, str(tmp_path))
