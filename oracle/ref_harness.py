@@ -88,8 +88,10 @@ def _dropin_swaps():
                 sys.modules[k] = v
 
 
-def run_main(mode, model_path, out_dir, extra_argv=(), batches=None, dropin=False, stream_seed=0, top_p=1):
+def run_main(mode, model_path, out_dir, extra_argv=(), batches=None, dropin=False, stream_seed=0, top_p=1, midi_tail=False):
     """MuseDiffusion.run.sample.main(namespace), unmodified.  Returns dict(tokens=[...], masks=[...], step_ids, step_margin).
+    `midi_tail` (modification mode only — generation loops until enough rows are valid): `decode_batch` resolves to the
+    package's instead of the recorder, so the run ends in MIDI files.
     `batches`: modification mode's data loader replacement (list of cond dicts), SURVEY.md §8c item 4."""
     import torch
     install()
@@ -104,6 +106,13 @@ def run_main(mode, model_path, out_dir, extra_argv=(), batches=None, dropin=Fals
     def fake_decode_batch(mode, sequences, input_ids_mask_ori, output_dir, batch_index, previous_count, **kw):
         captured["tokens"].append(np.array(sequences))
         captured["masks"].append(np.array(input_ids_mask_ori))
+        if midi_tail:                                             # the fourth swap: the package's decode_batch writes the files
+            import musediffusion_b200.decode_util as our_decode
+            out = our_decode.decode_batch(mode, sequences, input_ids_mask_ori, batch_index, previous_count, output_dir,
+                                          return_indices=True, strict_validation=kw.get("strict_validation", False))
+            captured.setdefault("valid", []).append(out)
+            captured["output_dir"] = output_dir
+            return out
         return len(sequences), []
 
     stream = O.NoiseStream(stream_seed)

@@ -79,3 +79,22 @@ def test_reference_main_modification_dropin(checkpoint):
     ref = H.run_main("modification", model_path, out_dir, argv, batches=batches, stream_seed=8)
     got = H.run_main("modification", model_path, out_dir, argv, batches=batches, dropin=True, stream_seed=8)
     compare("modification / ddim50 x25", ref, got)
+
+
+def test_reference_main_ends_in_midi_files(checkpoint, capsys):
+    """fourth swap: `decode_batch` of the reference's main() resolves to the package's (GPU validity filter + MIDI writer);
+    the run's own bookkeeping (valid counts, log file) goes on as with the reference's decoder."""
+    model_path, out_dir = checkpoint
+    conds = [O.make_synthetic_batch("modification", 3, L, seed=30 + i) for i in range(2)]
+    batches = [{k: torch.from_numpy(v) for k, v in c.items()} for c in conds]
+    argv = ["--step", "20", "--batch_size", "3", "--strength", "0.5", "--use_corruption", "false"]
+    got = H.run_main("modification", model_path, out_dir, argv, batches=batches, dropin=True, stream_seed=9, midi_tail=True)
+    assert len(got["valid"]) == 2
+    files = sorted(f for f in os.listdir(got["output_dir"]) if f.endswith(".midi"))
+    want = []
+    for b, (count, invalid) in enumerate(got["valid"]):
+        assert count + len(invalid) == 3
+        want += ["%07d_batch%05d_%04d.midi" % (b * 3 + k, b, k) for k in range(3) if k not in invalid]
+    assert files == sorted(want)
+    printed = capsys.readouterr().out
+    assert printed.count("Summary of Batch") >= 2
