@@ -126,6 +126,31 @@ def create_parser():
     return p
 
 
+def batch_metrics(total, prep, correct_ids, mask, batch_index):
+    """run/sample.py:244-280: ONNC over (ground truth + generated) note sequences of the batch's VALID rows, pitch / velocity
+    controllability of the generated ones; sums kept the way the reference weights them."""
+    from . import decode_util, metric
+    keep = [k for k in range(len(prep.status)) if prep.status[k] == decode_util.OK]
+    truth = decode_util.prepare_batch(torch.as_tensor(correct_ids).to(mask.device)[keep], mask[keep])
+    if any(ns is None for ns in truth.note_seqs):
+        raise decode_util.SequenceToMidiError("ground-truth row cannot be split into meta and notes")
+    generated, metas = [prep.note_seqs[k] for k in keep], [prep.metas[k] for k in keep]
+    onnc = float(metric.ONNC(tuple(truth.note_seqs) + tuple(generated), device=mask.device))
+    total_p, wrong_p = metric.Controllability_Pitch(metas, generated, device=mask.device)
+    total_v, wrong_v = metric.Controllability_Velocity(metas, generated, device=mask.device)
+    total["onnc_sum"] += len(keep) * onnc
+    total["onnc_count"] += len(keep)
+    total["total_total_p"] += total_p
+    total["total_wrong_p"] += wrong_p
+    total["total_total_v"] += total_v
+    total["total_wrong_v"] += wrong_v
+    print((" Metric of Batch %d " % batch_index).center(60, "="))
+    print((" ONNC: %.6f " % onnc).center(60))
+    print((" CP: %.6f " % (wrong_p / total_p)).center(60))
+    print((" CV: %.6f " % (wrong_v / total_v)).center(60))
+    print("=" * 60 + "\n")
+
+
 def pack_main(args):
     """`python -m musediffusion_b200 pack --model_path model_000000.pt`: checkpoint -> packed weight file (host only)."""
     from . import checkpoint
@@ -154,9 +179,12 @@ def main(argv=None):
     if args.mode == "generation":
         from .meta import meta_from_args, meta_to_batch
         midi_meta = meta_from_args(args)
+    correct_all = None
     if args.input_npz:
         data = np.load(args.input_npz)
         ids_all, mask_all = data["input_ids"], data["input_mask"]
+        if args.mode == "modification" and "correct_ids" in data.files:      # data/wrapper.py:118-124: what the loader keeps
+            correct_all = data["correct_ids"]                                # beside the (possibly corrupted) input_ids
     elif midi_meta is not None:                                   # run/sample.py:117-121: every sample from the one meta
         b = meta_to_batch(midi_meta, args.num_samples, targs.seq_len)
         ids_all, mask_all = b["input_ids"].numpy(), b["input_mask"].numpy()
@@ -165,6 +193,11 @@ def main(argv=None):
         n = args.num_samples if args.mode == "generation" else args.batch_size * args.num_batches
         b = make_synthetic_batch(args.mode, n, targs.seq_len, seed=args.sample_seed)
         ids_all, mask_all = b["input_ids"], b["input_mask"]
+        # the synthetic prefixes draw every meta token from its whole range, "unknown" included; a MIDI file cannot carry an
+        # unknown tempo / key / time signature (the reference's writer raises on them), so the stand-in input takes the first
+        # known class instead
+        for col, unknown in ((0, 560), (1, 601), (2, 626)):
+            ids_all[:, col] = np.where(ids_all[:, col] == unknown, unknown + 1, ids_all[:, col])
     out_dir = os.path.join(args.out_dir, os.path.basename(os.path.dirname(os.path.abspath(args.model_path))),
                            os.path.basename(args.model_path) + "." + args.mode + ".samples")
     os.makedirs(out_dir, exist_ok=True)
@@ -194,16 +227,26 @@ def main(argv=None):
         # decode_batch (utils/decode_util.py:233-384) on the gathered ids: one launch per batch for the token-level half, then one
         # MIDI file per valid row, named and numbered like the reference's
         flat, statuses, valid = [], [], 0
+        metric_total = dict(onnc_sum=0.0, onnc_count=0, total_total_p=0, total_wrong_p=0, total_total_v=0, total_wrong_v=0)
         for bi, tok in rows:
             mask = torch.from_numpy(mask_all[bi * args.batch_size: bi * args.batch_size + tok.shape[0]]).to(dev)
             prep = decode_util.prepare_batch(tok, mask, strict_validation=args.strict_validation)
             flat.append(tok.cpu().numpy().astype(np.int64))
             statuses.append(prep.status)
-            valid += decode_util.decode_batch(args.mode, tok, mask, batch_index=bi, output_dir=out_dir,
-                                              previous_count=valid if args.mode == "generation" else bi * args.batch_size,
-                                              strict_validation=args.strict_validation, prepared=prep)
+            n_valid = decode_util.decode_batch(args.mode, tok, mask, batch_index=bi, output_dir=out_dir,
+                                               previous_count=valid if args.mode == "generation" else bi * args.batch_size,
+                                               strict_validation=args.strict_validation, prepared=prep)
+            valid += n_valid
+            if correct_all is not None and n_valid:
+                batch_metrics(metric_total, prep, correct_all[bi * args.batch_size: bi * args.batch_size + tok.shape[0]], mask, bi)
         np.save(os.path.join(out_dir, "tokens.npy"), np.concatenate(flat, axis=0))
         np.save(os.path.join(out_dir, "decode_status.npy"), np.concatenate(statuses))
+        if correct_all is not None and metric_total["onnc_count"]:                # run/sample.py:303-311
+            print(" Total Metric ".center(60, "="))
+            print((" ONNC: %.6f " % (metric_total["onnc_sum"] / metric_total["onnc_count"])).center(60))
+            print((" CP: %.6f " % (metric_total["total_wrong_p"] / metric_total["total_total_p"])).center(60))
+            print((" CV: %.6f " % (metric_total["total_wrong_v"] / metric_total["total_total_v"])).center(60))
+            print("=" * 60 + "\n")
         print("### Total takes %.2fs; %d sequences (%d valid) -> %s"
               % (time.time() - tic, sum(len(t) for t in flat), valid, out_dir))
     dist.barrier()

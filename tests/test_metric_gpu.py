@@ -85,3 +85,30 @@ def test_sequences_the_reference_raises_on():
         metric.get_vectors(bad[1], device=DEV)
     with pytest.raises(ValueError):
         metric.ONNC([good, bad[0]], device=DEV)
+
+
+def test_cli_batch_metrics_accumulate_like_the_reference(golden_dir, capsys):
+    """sample.batch_metrics (run/sample.py:244-280): ONNC over ground truth + generated of the VALID rows, CP / CV of the
+    generated ones, ONNC weighted by the valid count."""
+    from musediffusion_b200 import decode_util, metric, sample
+    g = np.load(os.path.join(golden_dir, "decode_prepare.npz"))
+    dev = torch.device("cuda:0")
+    ok = [b for b in range(len(g["status_0"])) if g["status_0"][b] == 0]
+    notes = [g["notes_0"][b, :g["note_len_0"][b]] for b in ok]
+    _, status, _ = metric._run(notes, device=dev)
+    rows = [b for b, s in zip(ok, status.cpu().numpy()) if s == 0][:10]
+    assert len(rows) >= 6
+    rows = rows + [b for b in range(len(g["status_0"])) if g["status_0"][b] == 3][:2]        # two invalid rows ride along
+    tok, mask = torch.from_numpy(g["tokens"][rows]).to(dev), torch.from_numpy(g["masks"][rows]).to(dev)
+    prep = decode_util.prepare_batch(tok, mask)
+    total = dict(onnc_sum=0.0, onnc_count=0, total_total_p=0, total_wrong_p=0, total_total_v=0, total_wrong_v=0)
+    sample.batch_metrics(total, prep, g["tokens"][rows], mask, 4)
+    n = len(rows) - 2
+    gen = [prep.note_seqs[k] for k in range(n)]
+    metas = [prep.metas[k] for k in range(n)]
+    onnc = float(metric.ONNC(tuple(gen) + tuple(gen), device=dev))
+    assert total["onnc_count"] == n and abs(total["onnc_sum"] - n * onnc) < 1e-6
+    assert (total["total_total_p"], total["total_wrong_p"]) == metric.Controllability_Pitch(metas, gen, device=dev)
+    assert (total["total_total_v"], total["total_wrong_v"]) == metric.Controllability_Velocity(metas, gen, device=dev)
+    out = capsys.readouterr().out
+    assert "Metric of Batch 4" in out and "ONNC: %.6f" % onnc in out
