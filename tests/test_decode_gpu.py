@@ -126,6 +126,20 @@ def test_cli_generation_end_to_end(tmp_path, capsys):
     assert printed.count("Summary of Trial") == 2
     assert "(%d valid)" % int((status == 0).sum()) in printed
     assert sorted(f for f in os.listdir(d) if f.endswith(".midi")) == ["generated_%07d.midi" % k for k in range(int((status == 0).sum()))]
+    # the reference's meta flags (config/sample.py:157-254) instead of the synthetic prefix
+    from musediffusion_b200 import meta
+    flags = {"bpm": 70, "audio_key": "aminor", "time_signature": "4/4", "pitch_range": "mid_high", "num_measures": 8,
+             "inst": "acoustic_piano", "genre": "newage", "min_velocity": 60, "max_velocity": 80, "track_role": "main_melody",
+             "rhythm": "standard", "chord_progression": "Am-Am-Am-Am-G-G-G-G-F-F-F-F-E-E-E-E"}
+    argv = []
+    for k, v in flags.items():
+        argv += ["--" + k, str(v)]
+    out2 = tmp_path / "out2"
+    sample.main(["generation", "--model_path", str(ck / "model_000001.pt"), "--step", "20", "--batch_size", "2",
+                 "--num_samples", "3", "--out_dir", str(out2)] + argv)
+    tokens = np.load(out2 / "run1" / "model_000001.pt.generation.samples" / "tokens.npy")
+    prefix = meta.meta_to_sequence(flags)
+    assert tokens.shape == (3, 64) and (tokens[:, :len(prefix)] == np.array(prefix)).all()
 
 
 @pytest.mark.parametrize("mode", ["modification", "generation"])
