@@ -349,8 +349,11 @@ def bert_layer(p: Dict[str, np.ndarray], pre: str, h: np.ndarray, num_heads: int
 
 
 def denoiser_forward(p: Dict[str, np.ndarray], x: np.ndarray, timesteps: np.ndarray,
-                     num_heads: int = 12, hidden_t_dim: int = 128) -> np.ndarray:
-    """TransformerNetModel.forward (network.py:131-158); `p` uses the reference state-dict keys."""
+                     num_heads: int = 12, hidden_t_dim: int = None) -> np.ndarray:
+    """TransformerNetModel.forward (network.py:131-158); `p` uses the reference state-dict keys.  hidden_t_dim defaults to
+    the input width of time_embed.0 (network.py:57-61: the sinusoid is hidden_t_dim wide)."""
+    if hidden_t_dim is None:
+        hidden_t_dim = p["time_embed.0.weight"].shape[1]
     x = x.astype(F32)
     B, L, _ = x.shape
     emb_t = _linear(_silu(_linear(timestep_embedding(timesteps, hidden_t_dim),
