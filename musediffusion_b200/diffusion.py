@@ -93,6 +93,34 @@ def _extract_into_tensor(arr, timesteps, broadcast_shape):
 
 
 # ------------------------------------------------------------------------------------------------ diffusion
+_capture_state = {}          # device index -> [most recent graph, capture stream], kept for the life of the process
+
+
+def _capture(dev, fn):
+    """Record `fn`'s launches into a new CUDA graph.  Plain capture_begin / capture_end on a side stream instead of the
+    `torch.cuda.graph` context: the context empties the caching allocator (device and pinned host) on entry, which at
+    the bench size means returning and re-acquiring ~10 GB of step activations on EVERY sampling call (60-230 ms per
+    call, measured with tools/e2e_overhead.py).  Every capture on a device allocates from the memory pool of the previous
+    one (which is kept alive until the new graph exists, so the pool never dies): the step's temporaries are free blocks
+    of that pool again by the time a capture ends, and the next call's capture takes the same blocks.  Only the newest
+    graph of a device is ever replayed."""
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    state = _capture_state.setdefault(index, [None, torch.cuda.Stream(device=dev)])
+    previous, side = state
+    graph = torch.cuda.CUDAGraph()
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        graph.capture_begin(pool=previous.pool() if previous is not None else torch.cuda.graph_pool_handle())
+        try:
+            fn()
+        finally:
+            graph.capture_end()
+    main.wait_stream(side)
+    state[0] = graph
+    return graph
+
+
 class GaussianDiffusion:
     """Sampling utilities with the reference's attribute and method names (diffusion.py:121-901)."""
 
@@ -422,10 +450,7 @@ class GaussianDiffusion:
             else:
                 if graph is None:
                     before = ops.launch_count()
-                    torch.cuda.synchronize(dev)
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        one_step()
+                    graph = _capture(dev, one_step)
                     nodes = ops.launch_count() - before          # kernels recorded by the capture (nothing ran yet)
                     ops.add_launches(-nodes)
                 graph.replay()
