@@ -119,11 +119,28 @@ def create_parser():
         if name == "modification":
             sp.add_argument("--strength", type=float, default=0.75)
             sp.add_argument("--num_batches", type=int, default=1)
+            boolean = lambda s: s.lower() in ("1", "true", "yes")                     # noqa: E731
+            # config/sample.py:139-153: each defaults to the value in training_args.json
+            sp.add_argument("--use_corruption", type=boolean, default=None)
+            sp.add_argument("--corr_available", type=str, default=None)
+            sp.add_argument("--corr_max", type=int, default=None)
+            sp.add_argument("--corr_p", type=float, default=None)
+            sp.add_argument("--corr_kwargs", type=str, default=None)
         else:
             sp.add_argument("--num_samples", type=int, default=1000)
             from .meta import add_meta_arguments
             add_meta_arguments(sp)                       # config/sample.py:223-230: --bpm ... --chord_progression / --meta_json
     return p
+
+
+def corruption_from_args(args, targs):
+    """run/sample.py:125-135 + config/sample.py:150-153: corruption flags left unset take the training run's values; returns
+    the `Corruptions` callable or None when corruption is off."""
+    from .corruption import Corruptions
+    pick = lambda k: getattr(args, k, None) if getattr(args, k, None) is not None else getattr(targs, k, None)   # noqa: E731
+    if not pick("use_corruption"):
+        return None
+    return Corruptions.from_config(pick("corr_available"), pick("corr_max"), pick("corr_p"), pick("corr_kwargs"))
 
 
 def batch_metrics(total, prep, correct_ids, mask, batch_index):
@@ -185,6 +202,13 @@ def main(argv=None):
         ids_all, mask_all = data["input_ids"], data["input_mask"]
         if args.mode == "modification" and "correct_ids" in data.files:      # data/wrapper.py:118-124: what the loader keeps
             correct_all = data["correct_ids"]                                # beside the (possibly corrupted) input_ids
+        elif args.mode == "modification":
+            corruption = corruption_from_args(args, targs)
+            if corruption is not None:                                        # data/wrapper.py:73-86: row by row, in order
+                correct_all, ids_all = ids_all, np.array(ids_all)
+                lengths = data["length"] if "length" in data.files else (ids_all != 0).cumsum(1).argmax(1) + 1
+                for row, n in zip(ids_all, lengths):
+                    row[:n] = corruption(row[:n])
     elif midi_meta is not None:                                   # run/sample.py:117-121: every sample from the one meta
         b = meta_to_batch(midi_meta, args.num_samples, targs.seq_len)
         ids_all, mask_all = b["input_ids"].numpy(), b["input_mask"].numpy()

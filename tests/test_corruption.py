@@ -50,3 +50,19 @@ def test_seed_all_seeds_the_corruption_stream_and_edge_cases():
         C.random_rotating(row, 1)                                        # fewer than two bars (corruption.py:176)
     with pytest.raises(AssertionError):
         C.Corruptions(("mt",), 2, 0.5)                                   # corr_max > len(corr_available)
+
+
+def test_cli_corruption_flags_default_to_the_training_run(golden_dir):
+    """run/sample.py:125-135: --use_corruption / --corr_* left unset take training_args.json's values."""
+    import json
+    from types import SimpleNamespace
+    from musediffusion_b200.sample import corruption_from_args, create_parser
+    targs = SimpleNamespace(**json.load(open(os.path.join(golden_dir, "training_args_default.json"))))
+    args = create_parser().parse_args(["modification", "--model_path", "m.pt"])
+    c = corruption_from_args(args, targs)
+    assert c is not None and (c.corr_max, c.corr_p, len(c.corr_available)) == (targs.corr_max, targs.corr_p, 4)
+    args = create_parser().parse_args(["modification", "--model_path", "m.pt", "--corr_available", "mt,rr", "--corr_max", "1", "--corr_p", "1.0"])
+    c = corruption_from_args(args, targs)
+    assert (c.corr_max, c.corr_p, len(c.corr_available)) == (1, 1.0, 2)
+    args = create_parser().parse_args(["modification", "--model_path", "m.pt", "--use_corruption", "false"])
+    assert corruption_from_args(args, targs) is None
