@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
@@ -87,8 +87,14 @@ class ClockSampler(threading.Thread):
         sm = sorted(int(float(s[0])) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+               "samples": len(sm)}
+        try:                                                    # board power next to its limit: the step runs AT the cap
+            watts = sorted(float(s[6]) for s in self.samples if len(s) >= 8)
+            out["power_w"], out["power_limit_w"] = watts[len(watts) // 2], float(self.samples[0][7])
+        except (ValueError, IndexError):
+            pass
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
