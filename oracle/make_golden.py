@@ -581,6 +581,15 @@ def main():
         golden_loop_base("loop_base_gen_ddpm24.npz", "generation", 2, 21, 24, 24)
         golden_loop_base("loop_base_mod_ddim100.npz", "modification", 2, 22, 2000, 100, strength=1.0)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "base_b4":
+        # BASELINE.json configs[0] at its own batch size: 4 sequences x 2096, modification, --step 100 (DDIM gap 20), strength 1.0;
+        # ~15 min on 8 cores.  Ids + margins only (the B = 2 fixture above also pins the final sample).
+        import torch
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        golden_loop_base("loop_base_mod_ddim100_b4.npz", "modification", 4, 24, 2000, 100, strength=1.0, store_x_noised=False,
+                         store_final=False)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "base_ddpm":
         # the bench's own operating regime (BASELINE.json configs[1]): modification, 2000-step table, DDPM with truncated noise,
         # rounding every step, the first 40 indices from the top of the chain (strength 0.02 -> t_enc = 40); ~4 min on 8 cores

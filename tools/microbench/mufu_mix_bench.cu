@@ -52,5 +52,7 @@ int main() {
         if (w == 4) { run<0>("ex2 only", 4); run<1>("+ FFMA2 argument", 4); run<2>("+ FADD2 row sum", 4); run<3>("+ F2FP pack (full softmax mix)", 4); }
         else { run<0>("ex2 only", 8); run<3>("full softmax mix", 8); }
     }
+    run<3>("full softmax mix", 12);
+    run<3>("full softmax mix", 16);
     return 0;
 }
